@@ -1,0 +1,56 @@
+"""GPU integration: Tracker vs OracleTracker on a synthetic clip (config 1 scale)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import OracleTracker, pf
+from gpu_util import cuda
+
+pytestmark = pytest.mark.gpu
+
+
+def test_teacher_forced_and_free_running_ti():
+    from vitparticlefiltertracker_b200 import Tracker
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+    cuda()
+    frames, gt = make_clip("box", 224, 224, 32, seed=0, target=(48, 48))
+    n = 256
+    ora = OracleTracker("vit_tiny_patch16_224", n, seed=0)
+    trk = Tracker("vit_tiny_patch16_224", n, seed=0)
+    ora.init(frames[0], gt[0])
+    trk.init(frames[0], gt[0])
+    tm = torch.nn.functional.cosine_similarity(trk.template.cpu(), torch.from_numpy(ora.template), 0)
+    assert tm > 1 - 1e-3
+    assert np.abs(trk.particles.cpu().numpy() - ora.particles).max() < 2e-5
+    for t in range(1, 4):
+        # teacher forcing: start every frame from the oracle's particle set
+        trk.particles.copy_(torch.from_numpy(ora.particles))
+        so = ora.step(frames[t])
+        sg = trk.step(frames[t])
+        assert sg.frame_idx == so.frame_idx == t and trk.last_u == ora.last["u"]
+        assert np.abs(trk.propagated.cpu().numpy() - ora.last["propagated"]).max() < 2e-5
+        cos_g = (trk.logw.cpu().numpy() * np.float32(0.1))
+        dcos = np.abs(cos_g - ora.last["cos"]).max()
+        wg = trk.weights.cpu().numpy()
+        relw = np.abs(wg / ora.last["w"] - 1).max()
+        print(f"frame {t}: |dcos| {dcos:.2e}  weights rel {relw:.2e}  ess {sg.ess:.1f}/{so.ess:.1f}")
+        assert dcos < 5e-3                       # bf16 encoder vs fp32 oracle (D12: state honestly)
+        assert np.abs(np.array(sg.bbox) - np.array(so.bbox)).max() < 0.5
+        assert abs(sg.ess - so.ess) / so.ess < 0.15
+        # resampling is bit-exact given the GPU's own weights and the shared uniform
+        want_idx = pf.systematic_resample(wg, trk.last_u)
+        assert np.array_equal(trk.idx.cpu().numpy(), want_idx)
+    # free running for a few frames: estimates stay finite and inside the frame
+    for t in range(4, 10):
+        s = trk.step(frames[t])
+        assert np.isfinite(s.bbox).all() and 1 <= s.ess <= n
+
+
+def test_step_before_init_raises_and_bad_frame():
+    from vitparticlefiltertracker_b200 import Tracker
+    cuda()
+    trk = Tracker("vit_tiny_patch16_224", 64)
+    with pytest.raises(RuntimeError):
+        trk.step(np.zeros((32, 32, 3), np.uint8))
+    with pytest.raises(ValueError):
+        trk.init(np.zeros((32, 32), np.uint8), (0, 0, 8, 8))

@@ -1,0 +1,9 @@
+"""B200-native ViT particle-filter tracking hot path (sm_100a CUDA behind a C ABI).
+
+Public surface: ``Tracker.init(frame, bbox)`` / ``Tracker.step(frame) -> State``.
+"""
+from .tracker import State, Tracker  # noqa: F401
+from .vit_weights import VIT_CONFIGS, flops_per_crop, init_state_dict, pack_for_device  # noqa: F401
+
+__all__ = ["Tracker", "State", "VIT_CONFIGS", "flops_per_crop", "init_state_dict",
+           "pack_for_device"]

@@ -1,0 +1,81 @@
+// Shared helpers for libvpf.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vpf.h"
+
+namespace vpf {
+
+// thread-local last-error message, read through vpf_last_error()
+void set_error(const char* fmt, ...);
+
+#define VPF_REQUIRE(cond, ...)                                                     \
+  do {                                                                             \
+    if (!(cond)) {                                                                 \
+      ::vpf::set_error(__VA_ARGS__);                                               \
+      return VPF_ERR_INVALID;                                                      \
+    }                                                                              \
+  } while (0)
+
+#define VPF_CUDA(call)                                                             \
+  do {                                                                             \
+    cudaError_t err__ = (call);                                                    \
+    if (err__ != cudaSuccess) {                                                    \
+      ::vpf::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,               \
+                       cudaGetErrorString(err__));                                 \
+      return VPF_ERR_CUDA;                                                         \
+    }                                                                              \
+  } while (0)
+
+#define VPF_LAUNCH_CHECK() VPF_CUDA(cudaGetLastError())
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- Philox4x32-10 (Random123 constants), shared by host and device ----------------------
+struct Philox4 {
+  uint32_t v[4];
+};
+
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                          uint32_t c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  Philox4 o;
+  o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+  return o;
+}
+
+}  // namespace vpf

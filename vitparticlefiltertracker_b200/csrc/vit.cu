@@ -1,0 +1,406 @@
+// K2: timm-style ViT/16 encoder on sm_100a.  Oracle: oracle/vit.py (SURVEY.md Appendix A D1;
+// upstream anchor README.md:7 "Vision Transformer (ViT) ... feature extraction").
+//
+// Per block:  LN1 -> QKV GEMM(+bias) -> fused attention -> proj GEMM(+bias+residual)
+//             LN2 -> FC1 GEMM(+bias+GELU) -> FC2 GEMM(+bias+residual)
+// Residual stream X is fp32 [n*197][D]; GEMM operands are bf16; accumulation fp32 in TMEM.
+#include "common.cuh"
+#include "gemm.cuh"
+#include "attention.cuh"
+
+#include <mutex>
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+
+namespace vpf {
+
+// ---------------------------------------------------------------------------------------------
+// error string (thread local)
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA descriptors: the driver entry point is resolved at run time (libvpf.so links only the
+// static CUDA runtime, so it loads on machines without a driver).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// bf16 row-major [rows][cols] matrix, tile = box_rows x 64 columns, 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols,
+                    uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return VPF_ERR_CUDA; }
+  if (((uintptr_t)ptr & 15) || (cols * 2) % 16) {
+    set_error("TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+    return VPF_ERR_INVALID;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return VPF_ERR_CUDA; }
+  return VPF_OK;
+}
+
+static int pick_block_n(int N) {
+  if (N % 256 == 0) return 256;
+  if (N % 192 == 0) return 192;
+  if (N % 128 == 0) return 128;
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BLOCK_N, int MODE>
+static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g,
+                         cudaStream_t s) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VPF_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N, MODE>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = ((g.M + kBlockM - 1) / kBlockM) * (g.N / BLOCK_N);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_bf16_kernel<BLOCK_N, MODE><<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(tmA, tmB, g);
+  VPF_LAUNCH_CHECK();
+  return VPF_OK;
+}
+
+template <int BLOCK_N>
+static int launch_gemm_n(const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, int mode,
+                         cudaStream_t s) {
+  switch (mode) {
+    case kBiasBf16: return launch_gemm_t<BLOCK_N, kBiasBf16>(a, b, g, s);
+    case kBiasGeluBf16: return launch_gemm_t<BLOCK_N, kBiasGeluBf16>(a, b, g, s);
+    case kBiasResidualF32: return launch_gemm_t<BLOCK_N, kBiasResidualF32>(a, b, g, s);
+    case kPatchEmbedF32: return launch_gemm_t<BLOCK_N, kPatchEmbedF32>(a, b, g, s);
+  }
+  set_error("gemm: unknown epilogue mode %d", mode);
+  return VPF_ERR_INVALID;
+}
+
+static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, int mode,
+                       cudaStream_t s) {
+  switch (pick_block_n(g.N)) {
+    case 256: return launch_gemm_n<256>(a, b, g, mode, s);
+    case 192: return launch_gemm_n<192>(a, b, g, mode, s);
+    case 128: return launch_gemm_n<128>(a, b, g, mode, s);
+  }
+  set_error("gemm: N=%d must be a multiple of 128", g.N);
+  return VPF_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row kept in registers (D <= 1024), fp32 statistics.
+template <typename OutT>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x,
+                                                         size_t row_stride,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta,
+                                                         OutT* __restrict__ out, int rows, int D) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nvec = D >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x + (size_t)row * row_stride);
+  float4 v[8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      v[i] = x4[idx];
+      sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  const float mean = warp_sum(sum) / (float)D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)D + 1e-6f);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+      float o0 = (v[i].x - mean) * rstd * g.x + b.x;
+      float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+      float o2 = (v[i].z - mean) * rstd * g.z + b.z;
+      float o3 = (v[i].w - mean) * rstd * g.w + b.w;
+      if (sizeof(OutT) == 2) {
+        uint2 p;
+        p.x = pack_bf16(o0, o1);
+        p.y = pack_bf16(o2, o3);
+        reinterpret_cast<uint2*>(out + (size_t)row * D)[idx] = p;
+      } else {
+        reinterpret_cast<float4*>(out + (size_t)row * D)[idx] = make_float4(o0, o1, o2, o3);
+      }
+    }
+  }
+}
+
+// X[crop*197][:] = cls + pos[0]
+__global__ void cls_init_kernel(float* __restrict__ X, const float* __restrict__ cls,
+                                const float* __restrict__ pos, int n_crops, int D) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_crops * D) return;
+  int crop = i / D, d = i - crop * D;
+  X[(size_t)crop * kTokens * D + d] = cls[d] + pos[d];
+}
+
+struct LayerW {
+  const float *ln1_g, *ln1_b, *qkv_b, *proj_b, *ln2_g, *ln2_b, *fc1_b, *fc2_b;
+  const void *qkv_w, *proj_w, *fc1_w, *fc2_w;
+  CUtensorMap m_qkv, m_proj, m_fc1, m_fc2;
+};
+
+}  // namespace vpf
+
+using namespace vpf;
+
+struct vpf_vit {
+  vpf_vit_config cfg;
+  bool has_weights = false, has_ws = false;
+  const void* patch_w = nullptr;
+  const float *patch_b = nullptr, *cls = nullptr, *pos = nullptr, *norm_g = nullptr,
+              *norm_b = nullptr;
+  CUtensorMap m_patch;
+  std::vector<LayerW> layers;
+  // workspace
+  float* X = nullptr;           // [max_rows][D] fp32 residual stream
+  __nv_bfloat16* Xn = nullptr;  // [max_rows][D] LN output / attention output
+  __nv_bfloat16* big = nullptr; // [max_rows][4D] qkv ([..][3D]) or fc1 output
+  // activation tensor maps, cached for the last n_crops
+  int maps_for = -1;
+  const void* maps_patches = nullptr;
+  CUtensorMap a_patches, a_xn, a_big;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+int vpf_abi_version(void) { return VPF_ABI_VERSION; }
+const char* vpf_last_error(void) { return g_err; }
+
+int vpf_vit_create(vpf_vit** out, const vpf_vit_config* cfg) {
+  VPF_REQUIRE(out && cfg, "vpf_vit_create: null argument");
+  VPF_REQUIRE(cfg->dim > 0 && cfg->dim % 64 == 0 && cfg->dim <= 1024 && cfg->depth > 0 &&
+                  cfg->heads > 0 && cfg->heads * 64 == cfg->dim && cfg->max_crops > 0,
+              "vpf_vit_create: need dim = 64*heads <= 1024, depth > 0, max_crops > 0");
+  if (!pick_block_n(cfg->dim) || !pick_block_n(3 * cfg->dim)) {
+    set_error("vpf_vit_create: dim %d unsupported (dim and 3*dim must be multiples of 128)", cfg->dim);
+    return VPF_ERR_UNSUPPORTED;
+  }
+  vpf_vit* h = new vpf_vit();
+  h->cfg = *cfg;
+  h->layers.resize(cfg->depth);
+  *out = h;
+  return VPF_OK;
+}
+
+int vpf_vit_destroy(vpf_vit* h) {
+  delete h;
+  return VPF_OK;
+}
+
+size_t vpf_vit_workspace_bytes(const vpf_vit_config* cfg) {
+  if (!cfg) return 0;
+  const size_t rows = (size_t)cfg->max_crops * kTokens, D = cfg->dim;
+  return align_up(rows * D * 4, 1024) + align_up(rows * D * 2, 1024) +
+         align_up(rows * 4 * D * 2, 1024) + 1024;
+}
+
+int vpf_vit_set_weights(vpf_vit* h, const void* const* p, int n) {
+  VPF_REQUIRE(h && p, "vpf_vit_set_weights: null argument");
+  const int D = h->cfg.dim, L = h->cfg.depth;
+  VPF_REQUIRE(n == VPF_VIT_N_GLOBAL + 12 * L + 2, "vpf_vit_set_weights: expected %d pointers, got %d",
+              VPF_VIT_N_GLOBAL + 12 * L + 2, n);
+  for (int i = 0; i < n; ++i) VPF_REQUIRE(p[i] != nullptr, "vpf_vit_set_weights: pointer %d is null", i);
+  int k = 0;
+  h->patch_w = p[k++]; h->patch_b = (const float*)p[k++];
+  h->cls = (const float*)p[k++]; h->pos = (const float*)p[k++];
+  int rc;
+  if ((rc = make_map(&h->m_patch, h->patch_w, D, 768, pick_block_n(D)))) return rc;
+  for (int l = 0; l < L; ++l) {
+    LayerW& w = h->layers[l];
+    w.ln1_g = (const float*)p[k++]; w.ln1_b = (const float*)p[k++];
+    w.qkv_w = p[k++]; w.qkv_b = (const float*)p[k++];
+    w.proj_w = p[k++]; w.proj_b = (const float*)p[k++];
+    w.ln2_g = (const float*)p[k++]; w.ln2_b = (const float*)p[k++];
+    w.fc1_w = p[k++]; w.fc1_b = (const float*)p[k++];
+    w.fc2_w = p[k++]; w.fc2_b = (const float*)p[k++];
+    if ((rc = make_map(&w.m_qkv, w.qkv_w, 3 * D, D, pick_block_n(3 * D)))) return rc;
+    if ((rc = make_map(&w.m_proj, w.proj_w, D, D, pick_block_n(D)))) return rc;
+    if ((rc = make_map(&w.m_fc1, w.fc1_w, 4 * D, D, pick_block_n(4 * D)))) return rc;
+    if ((rc = make_map(&w.m_fc2, w.fc2_w, D, 4 * D, pick_block_n(D)))) return rc;
+  }
+  h->norm_g = (const float*)p[k++]; h->norm_b = (const float*)p[k++];
+  h->has_weights = true;
+  return VPF_OK;
+}
+
+int vpf_vit_set_workspace(vpf_vit* h, void* ws, size_t bytes) {
+  VPF_REQUIRE(h && ws, "vpf_vit_set_workspace: null argument");
+  VPF_REQUIRE(((uintptr_t)ws & 1023) == 0, "vpf_vit_set_workspace: workspace must be 1024-byte aligned");
+  VPF_REQUIRE(bytes >= vpf_vit_workspace_bytes(&h->cfg),
+              "vpf_vit_set_workspace: need %zu bytes, got %zu", vpf_vit_workspace_bytes(&h->cfg), bytes);
+  const size_t rows = (size_t)h->cfg.max_crops * kTokens, D = h->cfg.dim;
+  uint8_t* b = (uint8_t*)ws;
+  h->X = (float*)b;            b += align_up(rows * D * 4, 1024);
+  h->Xn = (__nv_bfloat16*)b;   b += align_up(rows * D * 2, 1024);
+  h->big = (__nv_bfloat16*)b;
+  h->has_ws = true;
+  h->maps_for = -1;
+  return VPF_OK;
+}
+
+int vpf_vit_launches(const vpf_vit* h) {
+  if (!h) return 0;
+  return 2 /*cls, patch embed*/ + 7 * h->cfg.depth + 1 /*final LN*/;
+}
+
+int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* stream) {
+  VPF_REQUIRE(h && patches && emb, "vpf_vit_forward: null argument");
+  if (!h->has_weights || !h->has_ws) {
+    set_error("vpf_vit_forward: weights or workspace not set");
+    return VPF_ERR_STATE;
+  }
+  VPF_REQUIRE(n > 0 && n <= h->cfg.max_crops, "vpf_vit_forward: n_crops %d outside [1, %d]", n,
+              h->cfg.max_crops);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int D = h->cfg.dim, L = h->cfg.depth, H = h->cfg.heads;
+  const int M0 = n * 196, M = n * kTokens;
+  int rc;
+  if (h->maps_for != n || h->maps_patches != patches) {
+    if ((rc = make_map(&h->a_patches, patches, M0, 768, kBlockM))) return rc;
+    if ((rc = make_map(&h->a_xn, h->Xn, M, D, kBlockM))) return rc;
+    if ((rc = make_map(&h->a_big, h->big, M, 4 * D, kBlockM))) return rc;
+    h->maps_for = n;
+    h->maps_patches = patches;
+  }
+  static bool attn_attr = false;
+  if (!attn_attr) {
+    VPF_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kAttnSmem));
+    attn_attr = true;
+  }
+  const int ln_blocks = (M + 7) / 8;
+
+  cls_init_kernel<<<(n * D + 255) / 256, 256, 0, s>>>(h->X, h->cls, h->pos, n, D);
+  VPF_LAUNCH_CHECK();
+  {
+    GemmArgs g{M0, D, 768, h->patch_b, h->X, h->pos};
+    if ((rc = launch_gemm(h->a_patches, h->m_patch, g, kPatchEmbedF32, s))) return rc;
+  }
+  for (int l = 0; l < L; ++l) {
+    const LayerW& w = h->layers[l];
+    layernorm_kernel<__nv_bfloat16><<<ln_blocks, 256, 0, s>>>(h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D);
+    VPF_LAUNCH_CHECK();
+    {
+      GemmArgs g{M, 3 * D, D, w.qkv_b, h->big, nullptr};
+      if ((rc = launch_gemm(h->a_xn, w.m_qkv, g, kBiasBf16, s))) return rc;
+    }
+    attention_kernel<<<dim3(H, n), kAttnThreads, kAttnSmem, s>>>(h->big, h->Xn, D);
+    VPF_LAUNCH_CHECK();
+    {
+      GemmArgs g{M, D, D, w.proj_b, h->X, nullptr};
+      if ((rc = launch_gemm(h->a_xn, w.m_proj, g, kBiasResidualF32, s))) return rc;
+    }
+    layernorm_kernel<__nv_bfloat16><<<ln_blocks, 256, 0, s>>>(h->X, D, w.ln2_g, w.ln2_b, h->Xn, M, D);
+    VPF_LAUNCH_CHECK();
+    {
+      GemmArgs g{M, 4 * D, D, w.fc1_b, h->big, nullptr};
+      if ((rc = launch_gemm(h->a_xn, w.m_fc1, g, kBiasGeluBf16, s))) return rc;
+    }
+    {
+      GemmArgs g{M, D, 4 * D, w.fc2_b, h->X, nullptr};
+      if ((rc = launch_gemm(h->a_big, w.m_fc2, g, kBiasResidualF32, s))) return rc;
+    }
+  }
+  layernorm_kernel<float><<<(n + 7) / 8, 256, 0, s>>>(h->X, (size_t)kTokens * D, h->norm_g,
+                                                     h->norm_b, emb, n, D);
+  VPF_LAUNCH_CHECK();
+  return VPF_OK;
+}
+
+// ---- single-stage test hooks ----------------------------------------------------------------
+int vpf_gemm_bf16(const void* A, const void* W, const float* bias, void* out, const float* pos,
+                  int M, int N, int K, int mode, void* stream) {
+  VPF_REQUIRE(A && W && bias && out && M > 0 && N > 0 && K > 0, "vpf_gemm_bf16: bad arguments");
+  VPF_REQUIRE(K % kBlockK == 0, "vpf_gemm_bf16: K=%d must be a multiple of 64", K);
+  VPF_REQUIRE(mode != kPatchEmbedF32 || pos, "vpf_gemm_bf16: patch-embed mode needs pos");
+  const int bn = pick_block_n(N);
+  if (!bn) { set_error("vpf_gemm_bf16: N=%d must be a multiple of 128", N); return VPF_ERR_UNSUPPORTED; }
+  CUtensorMap ma, mb;
+  int rc;
+  if ((rc = make_map(&ma, A, M, K, kBlockM))) return rc;
+  if ((rc = make_map(&mb, W, N, K, bn))) return rc;
+  GemmArgs g{M, N, K, bias, out, pos};
+  return launch_gemm(ma, mb, g, mode, (cudaStream_t)stream);
+}
+
+int vpf_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows,
+                  int D, void* stream) {
+  VPF_REQUIRE(x && gamma && beta && out_bf16 && rows > 0 && D > 0 && D % 4 == 0 && D <= 1024,
+              "vpf_layernorm: bad arguments (D multiple of 4, <= 1024)");
+  layernorm_kernel<__nv_bfloat16><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+      x, D, gamma, beta, (__nv_bfloat16*)out_bf16, rows, D);
+  VPF_LAUNCH_CHECK();
+  return VPF_OK;
+}
+
+int vpf_attention(const void* qkv, void* out, int n_crops, int heads, void* stream) {
+  VPF_REQUIRE(qkv && out && n_crops > 0 && heads > 0, "vpf_attention: bad arguments");
+  VPF_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kAttnSmem));
+  attention_kernel<<<dim3(heads, n_crops), kAttnThreads, kAttnSmem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, heads * kHeadDim);
+  VPF_LAUNCH_CHECK();
+  return VPF_OK;
+}
+
+}  // extern "C"

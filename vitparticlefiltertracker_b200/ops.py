@@ -1,0 +1,187 @@
+"""Host-side wrappers: torch CUDA tensors in, libvpf.so (C ABI, include/vpf.h) out.
+
+PyTorch is plumbing only (device memory, streams); every computation below runs in the
+hand-written sm_100a kernels.  All calls enqueue on the current torch stream and do not sync.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+N_PATCH = 196
+PATCH_K = 768
+TOKENS = 197
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t: torch.Tensor, dtype) -> torch.Tensor:
+    assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), (t.device, t.dtype, dtype)
+    return t
+
+
+# ---- particle filter ---------------------------------------------------------------------------
+def init_particles(state, cx, cy, sigma_init, seed, stream_id=0, id_offset=0):
+    _dev(state, torch.float32)
+    n = state.shape[1]
+    _lib.check(_lib.load().vpf_init_particles(state.data_ptr(), n, state.stride(0), cx, cy,
+                                              sigma_init, seed, stream_id, id_offset, _stream()),
+               "vpf_init_particles")
+
+
+def propagate(state, sigma_pos, sigma_vel, sigma_scale, seed, frame_idx, stream_id=0, id_offset=0):
+    _dev(state, torch.float32)
+    n = state.shape[1]
+    _lib.check(_lib.load().vpf_propagate(state.data_ptr(), n, state.stride(0), sigma_pos, sigma_vel,
+                                         sigma_scale, seed, frame_idx, stream_id, id_offset,
+                                         _stream()), "vpf_propagate")
+
+
+def philox_fill(n, id_offset, c1, c2, c3, seed, device="cuda"):
+    out = torch.empty((4, n), dtype=torch.int32, device=device)
+    _lib.check(_lib.load().vpf_philox_fill(out.data_ptr(), n, id_offset, c1, c2, c3, seed,
+                                           _stream()), "vpf_philox_fill")
+    return out
+
+
+def normals_fill(n, id_offset, frame_idx, stream_id, seed, device="cuda"):
+    out = torch.empty((6, n), dtype=torch.float32, device=device)
+    _lib.check(_lib.load().vpf_normals_fill(out.data_ptr(), n, id_offset, frame_idx, stream_id,
+                                            seed, _stream()), "vpf_normals_fill")
+    return out
+
+
+def resample_uniform(seed, frame_idx, stream_id=0) -> float:
+    return float(_lib.load().vpf_resample_uniform(seed, frame_idx, stream_id))
+
+
+# ---- crop --------------------------------------------------------------------------------------
+def crop_state(frame, state, w0, h0, out=None):
+    _dev(frame, torch.uint8)
+    _dev(state, torch.float32)
+    H, W, _ = frame.shape
+    n = state.shape[1]
+    if out is None:
+        out = torch.empty((n * N_PATCH, PATCH_K), dtype=torch.bfloat16, device=frame.device)
+    _lib.check(_lib.load().vpf_crop_state(frame.data_ptr(), H, W, state.data_ptr(), n,
+                                          state.stride(0), w0, h0, out.data_ptr(), _stream()),
+               "vpf_crop_state")
+    return out
+
+
+def crop_boxes(frame, boxes, out=None):
+    _dev(frame, torch.uint8)
+    _dev(boxes, torch.float32)
+    H, W, _ = frame.shape
+    n = boxes.shape[0]
+    if out is None:
+        out = torch.empty((n * N_PATCH, PATCH_K), dtype=torch.bfloat16, device=frame.device)
+    _lib.check(_lib.load().vpf_crop_boxes(frame.data_ptr(), H, W, boxes.data_ptr(), n,
+                                          out.data_ptr(), _stream()), "vpf_crop_boxes")
+    return out
+
+
+# ---- ViT stages (test hooks) ---------------------------------------------------------------------
+def gemm_bf16(a, w, bias, mode, out=None, pos=None):
+    """C = A[M,K] @ W[N,K]^T with epilogue `mode` (see include/vpf.h)."""
+    _dev(a, torch.bfloat16); _dev(w, torch.bfloat16); _dev(bias, torch.float32)
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        assert mode in (0, 1)
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _lib.check(_lib.load().vpf_gemm_bf16(a.data_ptr(), w.data_ptr(), bias.data_ptr(),
+                                         out.data_ptr(), _lib.ptr(pos), M, N, K, mode, _stream()),
+               "vpf_gemm_bf16")
+    return out
+
+
+def layernorm(x, gamma, beta):
+    _dev(x, torch.float32)
+    rows, D = x.shape
+    out = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().vpf_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                         out.data_ptr(), rows, D, _stream()), "vpf_layernorm")
+    return out
+
+
+def attention(qkv, n_crops, heads):
+    _dev(qkv, torch.bfloat16)
+    D = heads * 64
+    assert qkv.shape == (n_crops * TOKENS, 3 * D)
+    out = torch.empty((n_crops * TOKENS, D), dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(_lib.load().vpf_attention(qkv.data_ptr(), out.data_ptr(), n_crops, heads,
+                                         _stream()), "vpf_attention")
+    return out
+
+
+# ---- likelihood / normalisation / resampling ---------------------------------------------------
+def loglik(emb, tmpl, tau, logw, local_max):
+    n, D = emb.shape
+    _lib.check(_lib.load().vpf_loglik(emb.data_ptr(), D, tmpl.data_ptr(), n, tau, logw.data_ptr(),
+                                      local_max.data_ptr(), _stream()), "vpf_loglik")
+
+
+def sumexp(logw, rank_max, local_sum):
+    _lib.check(_lib.load().vpf_sumexp(logw.data_ptr(), logw.numel(), rank_max.data_ptr(),
+                                      rank_max.numel(), local_sum.data_ptr(), _stream()),
+               "vpf_sumexp")
+
+
+def weights(logw, rank_max, rank_sum, state, w, cdf_local, total_local, stats):
+    _lib.check(_lib.load().vpf_weights(logw.data_ptr(), logw.numel(), rank_max.data_ptr(),
+                                       rank_sum.data_ptr(), rank_max.numel(), state.data_ptr(),
+                                       state.stride(0), w.data_ptr(), cdf_local.data_ptr(),
+                                       total_local.data_ptr(), stats.data_ptr(), _stream()),
+               "vpf_weights")
+
+
+def resample(cdf_all, totals, n_local, id_offset, u, state_all, state_out, idx):
+    R = totals.numel()
+    _lib.check(_lib.load().vpf_resample(cdf_all.data_ptr(), totals.data_ptr(), R, n_local,
+                                        id_offset, u, state_all.data_ptr(), state_out.data_ptr(),
+                                        state_out.stride(0), idx.data_ptr(), _stream()),
+               "vpf_resample")
+
+
+# ---- ViT encoder handle --------------------------------------------------------------------------
+class VitEncoder:
+    """Owns the opaque vpf_vit handle, the packed device weights and the workspace tensor."""
+
+    def __init__(self, dim, depth, heads, max_crops, packed_weights, device="cuda"):
+        lib = _lib.load()
+        self._lib = lib
+        self.dim, self.depth, self.heads, self.max_crops = dim, depth, heads, max_crops
+        self.cfg = _lib.VitConfig(dim, depth, heads, max_crops)
+        self._h = C.c_void_p()
+        _lib.check(lib.vpf_vit_create(C.byref(self._h), C.byref(self.cfg)), "vpf_vit_create")
+        self.weights = [t.to(device).contiguous() for t in packed_weights]   # keep alive
+        arr = (C.c_void_p * len(self.weights))(*[t.data_ptr() for t in self.weights])
+        _lib.check(lib.vpf_vit_set_weights(self._h, arr, len(self.weights)), "vpf_vit_set_weights")
+        nbytes = lib.vpf_vit_workspace_bytes(C.byref(self.cfg))
+        self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        base = self.workspace.data_ptr()
+        aligned = (base + 1023) // 1024 * 1024
+        _lib.check(lib.vpf_vit_set_workspace(self._h, aligned, nbytes), "vpf_vit_set_workspace")
+        self.launches = lib.vpf_vit_launches(self._h)
+
+    def forward(self, patches, n_crops, emb=None):
+        assert patches.is_cuda and patches.dtype == torch.bfloat16 and patches.is_contiguous()
+        if emb is None:
+            emb = torch.empty((n_crops, self.dim), dtype=torch.float32, device=patches.device)
+        _lib.check(self._lib.vpf_vit_forward(self._h, patches.data_ptr(), n_crops, emb.data_ptr(),
+                                             _stream()), "vpf_vit_forward")
+        return emb
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                self._lib.vpf_vit_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass

@@ -1,0 +1,208 @@
+"""Tracker: the drop-in Python surface of the hot path.
+
+The upstream repository defines no API; its I/O contract is README.md:42 ("provide the input
+data (e.g., video feed or images) ... output the tracked positions").  That is restated as
+``Tracker.init(frame, bbox)`` / ``Tracker.step(frame) -> State`` (OpenCV-tracker convention:
+bbox = (x, y, w, h), top-left, pixels).  Host code only moves pointers: every stage of a step
+runs in libvpf.so's sm_100a kernels on the current CUDA stream -- there is no CPU fallback.
+
+Step order (oracle/tracker.py, D11): propagate -> crop -> ViT -> weigh -> estimate ->
+resample -> gather.  ``init`` is frame 0, the first ``step`` is frame 1.
+
+Multi-GPU (``process_group``): particles are sharded by global id, rank r owns
+[r*n_local, (r+1)*n_local).  Per frame: all-gather of the local log-weight maxima, all-gather
+of the exact local exp-sums, and one all-gather of (weight total | local CDF | state) that
+feeds the global resampling CDF.  Every quantity exchanged is exact (max, grid-snapped fp64
+sums), so the particle trajectory is bit-identical for any number of ranks.
+"""
+from __future__ import annotations
+
+import math
+from typing import NamedTuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .vit_weights import VIT_CONFIGS, init_state_dict, pack_for_device
+
+
+class State(NamedTuple):
+    bbox: tuple      # (x, y, w, h) top-left, pixels
+    ess: float
+    frame_idx: int
+
+
+class Tracker:
+    def __init__(self, model="vit_base_patch16_224", n_particles=4096, seed=0, device="cuda",
+                 dtype=torch.bfloat16, tau=0.1, sigma_pos=None, sigma_vel=None, sigma_scale=0.01,
+                 sigma_init=None, state_dict=None, process_group=None, stream_id=0,
+                 encoder=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("Tracker needs a CUDA device: the hot path has no CPU fallback")
+        if dtype != torch.bfloat16:
+            raise ValueError("the sm_100a ViT path computes in bf16 with fp32 accumulation")
+        if model not in VIT_CONFIGS:
+            raise ValueError(f"unknown model {model!r}; choose from {sorted(VIT_CONFIGS)}")
+        self.model = model
+        self.device = torch.device(device)
+        self.seed = int(seed)
+        self.tau = float(tau)
+        self.stream_id = int(stream_id)
+        self._sig = (sigma_pos, sigma_vel, sigma_scale, sigma_init)
+        self.pg = process_group
+        if self.pg is not None:
+            import torch.distributed as dist
+            self.rank, self.world = dist.get_rank(self.pg), dist.get_world_size(self.pg)
+        else:
+            self.rank, self.world = 0, 1
+        self.n_global = int(n_particles)
+        if self.n_global % self.world:
+            raise ValueError("n_particles must be divisible by the number of ranks")
+        self.n = self.n_global // self.world          # local particles
+        self.id_offset = self.rank * self.n
+        cfg = VIT_CONFIGS[model]
+        self.dim = cfg["dim"]
+        if encoder is None:
+            sd = state_dict if state_dict is not None else init_state_dict(model)
+            encoder = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], self.n,
+                                     pack_for_device(model, sd), device=self.device)
+        assert encoder.max_crops >= self.n
+        self.encoder = encoder
+        dev, n, R = self.device, self.n, self.world
+        f32, f64 = torch.float32, torch.float64
+        self.particles = torch.zeros((6, n), dtype=f32, device=dev)
+        self._next = torch.zeros((6, n), dtype=f32, device=dev)
+        self.weights = torch.full((n,), 1.0 / self.n_global, dtype=f32, device=dev)
+        self.patches = torch.empty((n * ops.N_PATCH, ops.PATCH_K), dtype=torch.bfloat16, device=dev)
+        self.emb = torch.empty((n, self.dim), dtype=f32, device=dev)
+        self.logw = torch.empty((n,), dtype=f32, device=dev)
+        self.idx = torch.empty((n,), dtype=torch.int32, device=dev)
+        self.template = torch.zeros((self.dim,), dtype=f32, device=dev)
+        # exchange buffers ([R] slots; R = 1 on a single GPU, no collective is issued then)
+        self._max_local = torch.empty((1,), dtype=f32, device=dev)
+        self._max_all = torch.empty((R,), dtype=f32, device=dev) if R > 1 else self._max_local
+        self._sum_local = torch.empty((1,), dtype=f64, device=dev)
+        self._sum_all = torch.empty((R,), dtype=f64, device=dev) if R > 1 else self._sum_local
+        # packed per-rank record: [total (1 f64) | cdf (n f64) | state (6n f32 = 3n f64 slots)]
+        self._rec_len = 1 + n + 3 * n
+        self._rec_local = torch.empty((self._rec_len,), dtype=f64, device=dev)
+        self._rec_all = (torch.empty((R, self._rec_len), dtype=f64, device=dev) if R > 1 else None)
+        self._stats = torch.zeros((5,), dtype=f64, device=dev)
+        self._tbox = torch.empty((1, 4), dtype=f32, device=dev)
+        self.frame_idx = -1
+        self.launches_per_step = 0
+
+    # -- helpers -----------------------------------------------------------------------------
+    def _to_device_frame(self, frame):
+        if isinstance(frame, np.ndarray):
+            frame = torch.from_numpy(frame)
+        if frame.dtype != torch.uint8 or frame.dim() != 3 or frame.shape[2] != 3:
+            raise ValueError("frame must be uint8 [H, W, 3] RGB")
+        if not frame.is_cuda:
+            frame = frame.to(self.device, non_blocking=True)
+        return frame.contiguous()
+
+    def _rec_views(self, rec):
+        n = self.n
+        total = rec[0:1]
+        cdf = rec[1:1 + n]
+        state = rec[1 + n:].view(torch.float32).view(6, n)
+        return total, cdf, state
+
+    # -- API ---------------------------------------------------------------------------------
+    def init(self, frame, bbox) -> None:
+        frame = self._to_device_frame(frame)
+        x, y, w, h = [float(v) for v in bbox]
+        if w <= 0 or h <= 0:
+            raise ValueError("bbox width and height must be positive")
+        self.w0, self.h0 = w, h
+        scale = math.sqrt(w * h)
+        sp, sv, ss, si = self._sig
+        self.sigma_pos = float(np.float32(0.05 * scale if sp is None else sp))
+        self.sigma_vel = float(np.float32(0.02 * scale if sv is None else sv))
+        self.sigma_scale = float(np.float32(ss))
+        self.sigma_init = float(np.float32(0.1 * scale if si is None else si))
+        self._tbox.copy_(torch.tensor([[x + 0.5 * w, y + 0.5 * h, w, h]], dtype=torch.float32))
+        tp = ops.crop_boxes(frame, self._tbox)
+        self.encoder.forward(tp, 1, self.template.view(1, -1))
+        cx = float(np.float32(np.float32(x) + np.float32(0.5) * np.float32(w)))
+        cy = float(np.float32(np.float32(y) + np.float32(0.5) * np.float32(h)))
+        ops.init_particles(self.particles, cx, cy, self.sigma_init, self.seed, self.stream_id,
+                           self.id_offset)
+        self.weights.fill_(1.0 / self.n_global)
+        self.frame_idx = 0
+
+    def step(self, frame, _noise=None, _u=None, _emb=None) -> State:
+        """One tracked frame.  `_noise` ([6,n] normals), `_u` (resampling uniform) and `_emb`
+        ([n,D] embeddings) are test hooks that inject oracle quantities (teacher forcing)."""
+        if self.frame_idx < 0:
+            raise RuntimeError("call init(frame, bbox) before step(frame)")
+        frame = self._to_device_frame(frame)
+        self.frame_idx += 1
+        t = self.frame_idx
+        st = self.particles
+        # a3 motion
+        if _noise is None:
+            ops.propagate(st, self.sigma_pos, self.sigma_vel, self.sigma_scale, self.seed, t,
+                          self.stream_id, self.id_offset)
+        else:
+            self._propagate_with(_noise)
+        # a4 crop, a5 ViT
+        if _emb is None:
+            ops.crop_state(frame, st, self.w0, self.h0, self.patches)
+            self.encoder.forward(self.patches, self.n, self.emb)
+            emb = self.emb
+        else:
+            emb = _emb
+        # a6 likelihood + exact normalisation
+        ops.loglik(emb, self.template, self.tau, self.logw, self._max_local)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self._max_all, self._max_local, group=self.pg)
+        ops.sumexp(self.logw, self._max_all, self._sum_local)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._sum_all, self._sum_local, group=self.pg)
+        total, cdf, st_slot = self._rec_views(self._rec_local)
+        self._stats.zero_()
+        ops.weights(self.logw, self._max_all, self._sum_all, st, self.weights, cdf, total,
+                    self._stats)
+        # a7 + a8 resample + gather
+        u = ops.resample_uniform(self.seed, t, self.stream_id) if _u is None else float(_u)
+        if self.world > 1:
+            st_slot.copy_(st)
+            dist.all_gather_into_tensor(self._rec_all.view(-1), self._rec_local, group=self.pg)
+            dist.all_reduce(self._stats, group=self.pg)
+            R, n = self.world, self.n
+            totals = self._rec_all[:, 0].contiguous()
+            cdf_all = self._rec_all[:, 1:1 + n].contiguous()
+            state_all = self._rec_all[:, 1 + n:].contiguous().view(torch.float32).view(R, 6, n)
+        else:
+            totals, cdf_all, state_all = total, cdf, st
+        ops.resample(cdf_all, totals, self.n, self.id_offset, u, state_all, self._next, self.idx)
+        self.particles, self._next = self._next, self.particles
+        self.propagated = self._next            # pre-resampling state of this frame (tests)
+        self.last_u = u
+        # estimate: the only device->host read of the step
+        s = self._stats.tolist()
+        sw = s[0]
+        cx, cy, sc = s[2] / sw, s[3] / sw, s[4] / sw
+        ess = 1.0 / s[1] if s[1] > 0 else 0.0
+        w = self.w0 * math.exp(sc)
+        h = self.h0 * math.exp(sc)
+        return State((cx - 0.5 * w, cy - 0.5 * h, w, h), ess, t)
+
+    def _propagate_with(self, noise):
+        """Test hook: the motion update with externally supplied normals (torch elementwise on
+        the device; not part of the product path)."""
+        z = noise.to(self.device, torch.float32)
+        st = self.particles
+        sp, sv, ss = [torch.tensor(v, dtype=torch.float32, device=self.device)
+                      for v in (self.sigma_pos, self.sigma_vel, self.sigma_scale)]
+        new = st.clone()
+        new[0] = (st[0] + st[2]) + sp * z[0]
+        new[1] = (st[1] + st[3]) + sp * z[1]
+        new[2] = st[2] + sv * z[2]
+        new[3] = st[3] + sv * z[3]
+        new[4] = st[4] + ss * z[4]
+        st.copy_(new)

@@ -1,0 +1,80 @@
+"""ViT/16 weight handling for the tracker: model table, seeded init
+and packing of a timm-keyed state_dict into the pointer order libvpf expects (include/vpf.h).
+
+No pretrained checkpoints exist offline and the upstream repository ships none
+(/root/reference/README.md:7 names the model family only), so the default is a seeded random
+init; ``state_dict=`` accepts real timm weights (`vit_*_patch16_224`, num_classes=0).
+"""
+from __future__ import annotations
+
+import torch
+
+VIT_CONFIGS = {
+    "vit_tiny_patch16_224": dict(dim=192, depth=12, heads=3),
+    "vit_small_patch16_224": dict(dim=384, depth=12, heads=6),
+    "vit_base_patch16_224": dict(dim=768, depth=12, heads=12),
+    "vit_large_patch16_224": dict(dim=1024, depth=24, heads=16),
+}
+TOKENS = 197
+WEIGHT_SEED = 1234
+
+
+def flops_per_crop(model: str) -> float:
+    """Full forward, 2 FLOP/MAC, no padding: 2*196*768*D + L*(24*197*D^2 + 4*197^2*D)."""
+    c = VIT_CONFIGS[model]
+    d, l = c["dim"], c["depth"]
+    return 2.0 * 196 * 768 * d + l * (24.0 * TOKENS * d * d + 4.0 * TOKENS * TOKENS * d)
+
+
+def _block_keys(i):
+    p = f"blocks.{i}."
+    return [p + "norm1.weight", p + "norm1.bias", p + "attn.qkv.weight", p + "attn.qkv.bias",
+            p + "attn.proj.weight", p + "attn.proj.bias", p + "norm2.weight", p + "norm2.bias",
+            p + "mlp.fc1.weight", p + "mlp.fc1.bias", p + "mlp.fc2.weight", p + "mlp.fc2.bias"]
+
+
+def init_state_dict(model: str, seed: int = WEIGHT_SEED) -> dict:
+    """Weights / pos_embed trunc-normal(std .02, cut at +-.04), biases 0, LN (1, 0),
+    cls_token normal(std 1e-6); one CPU generator walked in timm key order."""
+    c = VIT_CONFIGS[model]
+    d, depth = c["dim"], c["depth"]
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+
+    def tn(*shape):
+        t = torch.empty(shape, dtype=torch.float32)
+        torch.nn.init.trunc_normal_(t, mean=0.0, std=0.02, a=-0.04, b=0.04, generator=g)
+        return t
+
+    sd = {"patch_embed.proj.weight": tn(d, 3, 16, 16),
+          "patch_embed.proj.bias": torch.zeros(d),
+          "cls_token": torch.empty(1, 1, d).normal_(0.0, 1e-6, generator=g),
+          "pos_embed": tn(1, TOKENS, d)}
+    for i in range(depth):
+        k = _block_keys(i)
+        sd[k[0]] = torch.ones(d); sd[k[1]] = torch.zeros(d)
+        sd[k[2]] = tn(3 * d, d); sd[k[3]] = torch.zeros(3 * d)
+        sd[k[4]] = tn(d, d); sd[k[5]] = torch.zeros(d)
+        sd[k[6]] = torch.ones(d); sd[k[7]] = torch.zeros(d)
+        sd[k[8]] = tn(4 * d, d); sd[k[9]] = torch.zeros(4 * d)
+        sd[k[10]] = tn(d, 4 * d); sd[k[11]] = torch.zeros(d)
+    sd["norm.weight"] = torch.ones(d)
+    sd["norm.bias"] = torch.zeros(d)
+    return sd
+
+
+def pack_for_device(model: str, sd: dict) -> list:
+    """timm state_dict -> list of CPU tensors in libvpf pointer order: GEMM weights bf16 [out][in]
+    (the K-major B operand), everything else fp32."""
+    c = VIT_CONFIGS[model]
+    d, depth = c["dim"], c["depth"]
+    f32 = lambda t: t.detach().to(torch.float32).contiguous()
+    bf = lambda t: t.detach().to(torch.float32).to(torch.bfloat16).contiguous()
+    out = [bf(sd["patch_embed.proj.weight"].reshape(d, 768)), f32(sd["patch_embed.proj.bias"]),
+           f32(sd["cls_token"].reshape(d)), f32(sd["pos_embed"].reshape(TOKENS, d))]
+    for i in range(depth):
+        for key in _block_keys(i):
+            t = sd[key]
+            out.append(bf(t) if (key.endswith("weight") and t.dim() == 2) else f32(t))
+    out += [f32(sd["norm.weight"]), f32(sd["norm.bias"])]
+    return out
