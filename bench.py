@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the ViT particle-filter tracking hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one tracked frame: Tracker.step(frame) = propagate -> crop -> ViT -> weigh ->
+resample for every particle.  Workload at N=1: BASELINE.json configs[2] (the headline
+single-GPU config): ViT-B/16, 4096 particles, systematic resampling every frame, synthetic
+1080p clip.  With N GPUs the particle set grows to 4096*N, sharded by global particle id (weak
+scaling, the shape of configs[3]); NCCL carries only the max / exp-sum / CDF exchange.
+
+value  = particle-updates/s (= particles x tracked frames/s), frames already resident in HBM.
+e2e    = the same through the public API with HOST frames: pinned host -> device copy of each
+         frame and the device -> host read of the state estimate are inside the timed region.
+roofline = the tcgen05 GEMM family (qkv/proj/fc1/fc2), timed live with CUDA events inside a
+         sustained loop, against MEASURED_PEAKS.json's sustained bf16 figure.
+cpu_baseline = the CPU oracle (a port: the upstream repo is a README only) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "particle_updates_per_s"
+UNIT = "particle-updates/s"
+MODEL = "vit_base_patch16_224"
+PARTICLES_PER_GPU = 4096
+FRAME_HW = (1080, 1920)
+TARGET = (96, 96)
+CLIP_FRAMES = 16
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops_burst=d["bf16_tflops"],
+                    tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0,
+                source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_run(steps, warmup, n_sample, frames, gt):
+    """Times the CPU oracle (all host threads) on a bounded sample: `n_sample` particles of the
+    same workload.  Returns (particle-updates/s, seconds per step, threads)."""
+    from oracle import OracleTracker
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    trk = OracleTracker(MODEL, n_sample, seed=0)
+    trk.init(frames[0], gt[0])
+    for i in range(warmup):
+        trk.step(frames[1 + i % (len(frames) - 1)])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        trk.step(frames[1 + (warmup + i) % (len(frames) - 1)])
+    dt = time.perf_counter() - t0
+    return n_sample * steps / dt, dt / steps, threads
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The upstream repo is a
+    README only, so this is the oracle port (oracle/), with every host thread torch can use."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+    frames, gt = make_clip("box", FRAME_HW[0], FRAME_HW[1], 6, seed=0, target=TARGET)
+    n_sample = 32
+    steps = max(1, min(args.steps, 4))
+    warmup = max(0, min(args.warmup, 1))
+    v, sec, threads = cpu_oracle_run(steps, warmup, n_sample, frames, gt)
+    sample = (f"OracleTracker (CPU PyTorch fp32), {n_sample} of {PARTICLES_PER_GPU} particles, "
+              f"{steps} frames of the same 1080p clip")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "frames_per_s_at_4096": v / PARTICLES_PER_GPU,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE configs[2]: ViT-B/16 @224, 4096 particles per GPU, systematic "
+                        "resampling every frame, synthetic 1080p moving-target clip",
+            "model": MODEL, "particles_per_gpu": PARTICLES_PER_GPU,
+            "particles_total": PARTICLES_PER_GPU * n_gpus, "frame": "1080x1920x3 uint8",
+            "parallelism": f"particle-sharded x{n_gpus}",
+            "l2": "per-step working set ~10 GB per GPU >> 126 MB L2 (inputs larger than L2)"}
+
+
+def gemm_roofline(dev, M, D, peaks, reps=2):
+    """Times every GEMM launch of a 12-block encoder pass (qkv, proj, fc1, fc2 at the real M)
+    with CUDA events on the launching stream, inside a sustained loop."""
+    from vitparticlefiltertracker_b200 import ops
+    xn = (torch.randn(M, D, device=dev) * 0.5).to(torch.bfloat16)
+    big = torch.empty(M, 4 * D, dtype=torch.bfloat16, device=dev)
+    X = torch.zeros(M, D, device=dev)
+    shapes = [("qkv", 3 * D, D, 0), ("proj", D, D, 2), ("fc1", 4 * D, D, 1), ("fc2", D, 4 * D, 2)]
+    ws = {n: ((torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16),
+              torch.zeros(N, device=dev)) for n, N, K, _ in shapes}
+    qkv_out = big.view(-1)[: M * 3 * D].view(M, 3 * D)
+
+    def one(name, N, K, mode):
+        w, b = ws[name]
+        a = big if name == "fc2" else xn
+        out = X if mode == 2 else (qkv_out if name == "qkv" else big)
+        ops.gemm_bf16(a, w, b, mode, out=out)
+
+    for name, N, K, mode in shapes:          # warm-up
+        one(name, N, K, mode)
+    torch.cuda.synchronize()
+    ev = []
+    for _ in range(reps):
+        for _blk in range(12):
+            for name, N, K, mode in shapes:
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                one(name, N, K, mode)
+                e.record()
+                ev.append((name, N, K, s, e))
+    torch.cuda.synchronize()
+    per = {}
+    for name, N, K, s, e in ev:
+        d = per.setdefault(name, {"ms": [], "flops": 2.0 * M * N * K})
+        d["ms"].append(s.elapsed_time(e))
+    tot_ms = sum(float(np.mean(d["ms"])) for d in per.values())
+    tot_fl = sum(d["flops"] for d in per.values())
+    detail = {k: {"ms": float(np.mean(d["ms"])),
+                  "tflops": d["flops"] / float(np.mean(d["ms"])) / 1e9} for k, d in per.items()}
+    achieved = tot_fl / tot_ms / 1e9
+    peak = peaks["tflops_sustained"]
+    return {"bound": "tensor", "kernel": "gemm_bf16_kernel<tcgen05> (qkv+proj+fc1+fc2 of one block)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": peaks["source"] + ", sustained bf16", "traffic": None,
+            "flops_per_launch_set": tot_fl, "ms_per_launch_set": tot_ms, "detail": detail}, tot_ms
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    from vitparticlefiltertracker_b200 import Tracker, flops_per_crop
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    n_gpus = world
+    n_total = PARTICLES_PER_GPU * n_gpus
+    peaks = load_peaks()
+
+    frames, gt = make_clip("box", FRAME_HW[0], FRAME_HW[1], CLIP_FRAMES, seed=0, target=TARGET)
+    frames_host = torch.from_numpy(frames).pin_memory()
+    frames_dev = torch.from_numpy(frames).to(dev)
+    trk = Tracker(MODEL, n_total, seed=0, device=dev, process_group=pg)
+    trk.init(frames_dev[0], gt[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(frames_src, steps, warmup):
+        for i in range(warmup):
+            trk.step(frames_src[1 + i % (CLIP_FRAMES - 1)])
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            trk.step(frames_src[1 + (warmup + i) % (CLIP_FRAMES - 1)])
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(frames_dev, args.steps, args.warmup)
+    ms_e2e = timed(frames_host, args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    roof, gemm_ms = gemm_roofline(dev, trk.n * 197, trk.dim, peaks) if rank == 0 else (None, 0.0)
+    barrier()
+
+    if rank == 0:
+        ms_step = ms_dev / args.steps
+        value = n_total * args.steps / (ms_dev / 1e3)
+        e2e_v = n_total * args.steps / (ms_e2e / 1e3)
+        fl = flops_per_crop(MODEL)
+        roof["share_of_step"] = gemm_ms * 12 / ms_step
+        launches_per_step = trk.encoder.launches + 8      # + propagate, crop, loglik(2), sumexp,
+        line = {                                          #   weights, resample, stats memset
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(n_gpus),
+            "frames_per_s": args.steps / (ms_dev / 1e3),
+            "step_tflops_per_gpu": trk.n * fl / (ms_step / 1e3) / 1e12,
+            "step_frac_of_sustained_peak": trk.n * fl / (ms_step / 1e3) / 1e12 / peaks["tflops_sustained"],
+            "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(frames_host[0].numel()),
+                    "d2h_bytes_per_step": 40},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roof, "clocks": clocks,
+        }
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            n_sample = 32
+            v, sec, threads = cpu_oracle_run(2, 1, n_sample, frames[:4], gt[:4])
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"OracleTracker (CPU PyTorch fp32): {n_sample} of {PARTICLES_PER_GPU} "
+                          f"particles, 2 timed frames of the same clip ({sec:.1f} s/frame)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
