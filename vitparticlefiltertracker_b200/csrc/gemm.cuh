@@ -7,7 +7,8 @@
 //               per stage; tcgen05.commit releases the stage and, after the last k-block,
 //               publishes the accumulator; owns the TMEM allocation (2 accumulator stages)
 //   warps 2-9   epilogue: tcgen05.ld the 128 x BLOCK_N fp32 accumulator (each warp: its 32-lane
-//               quarter x half of the columns), apply bias / GELU / residual / pos-embed, store.
+//               quarter x half of the columns), apply bias / GELU / residual / pos-embed, then
+//               transpose through a swizzled shared-memory slab so global access is coalesced.
 //               Runs concurrently with the MMAs of the next tile (double-buffered accumulators).
 //
 // Both operands are K-major (activations [M][K] row-major; nn.Linear weights [out][in]), so no
@@ -37,32 +38,53 @@ struct GemmArgs {
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;   // 64 bf16 = 128 B = one swizzle-128B row
 static constexpr int kUmmaK = 16;
-static constexpr int kGemmThreads = 320;  // 10 warps
-static constexpr int kEpiWarps = 8;
+static constexpr int kMaxEpiWarps = 16;
+
+// Epilogue warps: 4 TMEM lane quarters x kGroups column groups.  The bf16-output epilogues
+// (convert / GELU: ALU- and MUFU-heavy) get 4 warps per scheduler to hide latency; the fp32
+// read-modify-write epilogues are memory-bound and need registers for loads in flight.
+template <int BLOCK_N, int MODE>
+struct EpiCfg {
+  static constexpr int kGroups = (MODE <= 1) ? (BLOCK_N == 192 ? 3 : 4) : 2;
+  static constexpr int kWarps = 4 * kGroups;
+  static constexpr int kThreads = 64 + 32 * kWarps;
+  static constexpr int kColsPerWarp = BLOCK_N / kGroups;
+  static_assert(kColsPerWarp % 32 == 0, "epilogue column split must be a multiple of 32");
+};
 
 template <int BLOCK_N>
 struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192 ? 5 : 6);
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192 ? 4 : 5);
   static constexpr int kTmemCols = (2 * BLOCK_N > 256) ? 512 : 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSlabBytes = 4096;  // per epilogue warp: 32 rows x 128 B transpose slab
+  static constexpr int kEpiBytes = 8 * kSlabBytes;      // 8 x 4 KB (fp32) or 16 x 2 KB (bf16)
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-// erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below bf16 output rounding)
+// Exact (erf) GELU with erf by Abramowitz-Stegun 7.1.28: erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16,
+// |err| <= 3e-7 (measured: GELU abs err <= 9e-7, rel <= 4e-4 where |gelu| > 1e-3 -- 5x below
+// bf16 output rounding).  z = |x|/sqrt(2) is folded into the coefficients; one MUFU (rcp).
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = exp2f(-1.4426950408889634f * z * z);
-  const float erf_abs = fmaf(-p, e, 1.0f);
+  constexpr float c = 0.70710678118654752f;
+  constexpr float b1 = 0.0705230784f * c, b2 = 0.0422820123f * c * c,
+                  b3 = 0.0092705272f * c * c * c, b4 = 0.0001520143f * c * c * c * c,
+                  b5 = 0.0002765672f * c * c * c * c * c, b6 = 0.0000430638f * c * c * c * c * c * c;
+  const float ax = fabsf(x);
+  float p = fmaf(b6, ax, b5);
+  p = fmaf(p, ax, b4);
+  p = fmaf(p, ax, b3);
+  p = fmaf(p, ax, b2);
+  p = fmaf(p, ax, b1);
+  p = fmaf(p, ax, 1.0f);
+  p *= p; p *= p; p *= p; p *= p;               // ^16 (overflow -> inf -> rcp 0 -> erf 1)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
   const float hx = 0.5f * x;
-  return fmaf(copysignf(erf_abs, x), hx, hx);
+  return fmaf(copysignf(1.0f - r, x), hx, hx);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -70,13 +92,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Epilogue of one 32-column chunk of a warp's 32-row slab.
+//   phase 1 (thread = accumulator row, the tcgen05.ld 32x32b layout): bias (+GELU), convert,
+//           write the row into the warp's shared-memory slab, XOR-swizzled by 16-byte piece;
+//   phase 2 (transposed: consecutive lanes = consecutive 16-byte pieces of one row): read the
+//           slab back and touch global memory fully coalesced (a warp instruction covers whole
+//           64/128-byte row segments instead of 32 different cache lines).
 template <int MODE>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const GemmArgs& g, int row,
-                                               int col) {
-  // v: 32 consecutive fp32 accumulator columns [col, col+32) of output row `row`
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const GemmArgs& g,
+                                               uint8_t* slab, int row0, int col, int lane) {
   const float4* b4 = reinterpret_cast<const float4*>(g.bias + col);
   if (MODE == kBiasBf16 || MODE == kBiasGeluBf16) {
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.N + col;
+    // slab rows are 64 B (32 bf16): piece j of row r lives at r*64 + ((j ^ ((r>>1)&3)) << 4)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float f[8];
@@ -95,42 +122,79 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
       uint4 o;
       o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
       o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-      *reinterpret_cast<uint4*>(dst + q * 8) = o;
+      *reinterpret_cast<uint4*>(slab + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = o;
+    }
+    __syncwarp();
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(g.out);
+    const int p = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = i * 8 + (lane >> 2);
+      const uint4 val = *reinterpret_cast<const uint4*>(slab + r * 64 + ((p ^ ((r >> 1) & 3)) << 4));
+      const int grow = row0 + r;
+      if (grow < g.M)
+        *reinterpret_cast<uint4*>(out + (size_t)grow * g.N + col + p * 8) = val;
     }
   } else {
-    size_t orow = (size_t)row;
-    const float4* p4 = nullptr;
-    if (MODE == kPatchEmbedF32) {
-      int crop = row / 196, p = row - crop * 196;
-      orow = (size_t)crop * 197 + 1 + p;
-      p4 = reinterpret_cast<const float4*>(g.pos + (size_t)(1 + p) * g.N + col);
-    }
-    float4* x4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + orow * g.N + col);
+    // slab rows are 128 B (32 fp32): piece j of row r lives at r*128 + ((j ^ (r&7)) << 4)
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       float4 b = __ldg(b4 + q);
-      float4 r = (MODE == kPatchEmbedF32) ? __ldg(p4 + q) : x4[q];
       float4 o;
-      o.x = __uint_as_float(v[q * 4 + 0]) + b.x + r.x;
-      o.y = __uint_as_float(v[q * 4 + 1]) + b.y + r.y;
-      o.z = __uint_as_float(v[q * 4 + 2]) + b.z + r.z;
-      o.w = __uint_as_float(v[q * 4 + 3]) + b.w + r.w;
-      x4[q] = o;
+      o.x = __uint_as_float(v[q * 4 + 0]) + b.x;
+      o.y = __uint_as_float(v[q * 4 + 1]) + b.y;
+      o.z = __uint_as_float(v[q * 4 + 2]) + b.z;
+      o.w = __uint_as_float(v[q * 4 + 3]) + b.w;
+      *reinterpret_cast<float4*>(slab + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
+    }
+    __syncwarp();
+    float* X = reinterpret_cast<float*>(g.out);
+    const int p = lane & 7;
+    float4 res[8];
+    float4* dst[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {           // all global loads first: 8 independent requests
+      const int r = i * 4 + (lane >> 3);
+      const int grow = row0 + r;
+      dst[i] = nullptr;
+      if (grow < g.M) {
+        if (MODE == kPatchEmbedF32) {
+          const int crop = grow / 196, pp = grow - crop * 196;
+          dst[i] = reinterpret_cast<float4*>(X + ((size_t)crop * 197 + 1 + pp) * g.N + col) + p;
+          res[i] = __ldg(reinterpret_cast<const float4*>(g.pos + (size_t)(1 + pp) * g.N + col) + p);
+        } else {
+          dst[i] = reinterpret_cast<float4*>(X + (size_t)grow * g.N + col) + p;
+          res[i] = *dst[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3);
+      const float4 a = *reinterpret_cast<const float4*>(slab + r * 128 + ((p ^ (r & 7)) << 4));
+      if (dst[i]) {
+        float4 o;
+        o.x = a.x + res[i].x; o.y = a.y + res[i].y; o.z = a.z + res[i].z; o.w = a.w + res[i].w;
+        *dst[i] = o;
+      }
     }
   }
+  __syncwarp();   // slab is rewritten by the next chunk
 }
 
 template <int BLOCK_N, int MODE>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__((EpiCfg<BLOCK_N, MODE>::kThreads), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmArgs g) {
   using Cfg = GemmCfg<BLOCK_N>;
+  using Epi = EpiCfg<BLOCK_N, MODE>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle needs 1024-byte aligned tiles
   uint8_t* tiles = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kStages * Cfg::kStageBytes);
+  uint8_t* slabs = tiles + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slabs + Cfg::kEpiBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -146,7 +210,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], Epi::kWarps); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -206,10 +270,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue warps 2..9 =====================
+    // ===================== epilogue warps 2.. =====================
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;             // which half of the BLOCK_N columns
-    constexpr int kHalfCols = BLOCK_N / 2;
+    const int half = (warp - 2) >> 2;             // which column group of the BLOCK_N columns
+    constexpr int kHalfCols = Epi::kColsPerWarp;
+    constexpr int kSlab = (MODE <= 1) ? 2048 : 4096;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
@@ -217,7 +282,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_full[as], aphase, 3);
       tcgen05_fence_after();
-      const int row = m_blk * kBlockM + quarter * 32 + lane;
+      const int row0 = m_blk * kBlockM + quarter * 32;
+      uint8_t* slab = slabs + (warp - 2) * kSlab;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                              (uint32_t)(as * BLOCK_N + half * kHalfCols);
 #pragma unroll 1
@@ -225,8 +291,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t v[32];
         tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
         tmem_ld_wait();
-        if (row < g.M)
-          epilogue_chunk<MODE>(v, g, row, n_blk * BLOCK_N + half * kHalfCols + c * 32);
+        epilogue_chunk<MODE>(v, g, slab, row0, n_blk * BLOCK_N + half * kHalfCols + c * 32, lane);
       }
       tcgen05_fence_before();
       __syncwarp();

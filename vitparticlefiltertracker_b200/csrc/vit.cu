@@ -96,7 +96,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   }
   const int tiles = ((g.M + kBlockM - 1) / kBlockM) * (g.N / BLOCK_N);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_kernel<BLOCK_N, MODE><<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(tmA, tmB, g);
+  gemm_bf16_kernel<BLOCK_N, MODE><<<grid, EpiCfg<BLOCK_N, MODE>::kThreads, Cfg::kSmemBytes, s>>>(tmA, tmB, g);
   VPF_LAUNCH_CHECK();
   return VPF_OK;
 }

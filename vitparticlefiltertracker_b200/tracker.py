@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .exchange import Exchange, shard_range
 from .vit_weights import VIT_CONFIGS, init_state_dict, pack_for_device
 
 
@@ -57,10 +58,7 @@ class Tracker:
         else:
             self.rank, self.world = 0, 1
         self.n_global = int(n_particles)
-        if self.n_global % self.world:
-            raise ValueError("n_particles must be divisible by the number of ranks")
-        self.n = self.n_global // self.world          # local particles
-        self.id_offset = self.rank * self.n
+        self.id_offset, self.n = shard_range(self.n_global, self.rank, self.world)
         cfg = VIT_CONFIGS[model]
         self.dim = cfg["dim"]
         if encoder is None:
@@ -79,15 +77,7 @@ class Tracker:
         self.logw = torch.empty((n,), dtype=f32, device=dev)
         self.idx = torch.empty((n,), dtype=torch.int32, device=dev)
         self.template = torch.zeros((self.dim,), dtype=f32, device=dev)
-        # exchange buffers ([R] slots; R = 1 on a single GPU, no collective is issued then)
-        self._max_local = torch.empty((1,), dtype=f32, device=dev)
-        self._max_all = torch.empty((R,), dtype=f32, device=dev) if R > 1 else self._max_local
-        self._sum_local = torch.empty((1,), dtype=f64, device=dev)
-        self._sum_all = torch.empty((R,), dtype=f64, device=dev) if R > 1 else self._sum_local
-        # packed per-rank record: [total (1 f64) | cdf (n f64) | state (6n f32 = 3n f64 slots)]
-        self._rec_len = 1 + n + 3 * n
-        self._rec_local = torch.empty((self._rec_len,), dtype=f64, device=dev)
-        self._rec_all = (torch.empty((R, self._rec_len), dtype=f64, device=dev) if R > 1 else None)
+        self.xch = Exchange(self.pg, n, dev)
         self._stats = torch.zeros((5,), dtype=f64, device=dev)
         self._tbox = torch.empty((1, 4), dtype=f32, device=dev)
         self.frame_idx = -1
@@ -102,13 +92,6 @@ class Tracker:
         if not frame.is_cuda:
             frame = frame.to(self.device, non_blocking=True)
         return frame.contiguous()
-
-    def _rec_views(self, rec):
-        n = self.n
-        total = rec[0:1]
-        cdf = rec[1:1 + n]
-        state = rec[1 + n:].view(torch.float32).view(6, n)
-        return total, cdf, state
 
     # -- API ---------------------------------------------------------------------------------
     def init(self, frame, bbox) -> None:
@@ -155,28 +138,21 @@ class Tracker:
             emb = self.emb
         else:
             emb = _emb
-        # a6 likelihood + exact normalisation
-        ops.loglik(emb, self.template, self.tau, self.logw, self._max_local)
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(self._max_all, self._max_local, group=self.pg)
-        ops.sumexp(self.logw, self._max_all, self._sum_local)
-        if self.world > 1:
-            dist.all_gather_into_tensor(self._sum_all, self._sum_local, group=self.pg)
-        total, cdf, st_slot = self._rec_views(self._rec_local)
+        # a6 likelihood + exact normalisation (collectives are no-ops on a single GPU)
+        xch = self.xch
+        ops.loglik(emb, self.template, self.tau, self.logw, xch.max_local)
+        max_all = xch.gather_max()
+        ops.sumexp(self.logw, max_all, xch.sum_local)
+        sum_all = xch.gather_sum()
+        total, cdf, st_slot = xch.local_views()
         self._stats.zero_()
-        ops.weights(self.logw, self._max_all, self._sum_all, st, self.weights, cdf, total,
-                    self._stats)
+        ops.weights(self.logw, max_all, sum_all, st, self.weights, cdf, total, self._stats)
         # a7 + a8 resample + gather
         u = ops.resample_uniform(self.seed, t, self.stream_id) if _u is None else float(_u)
         if self.world > 1:
             st_slot.copy_(st)
-            dist.all_gather_into_tensor(self._rec_all.view(-1), self._rec_local, group=self.pg)
-            dist.all_reduce(self._stats, group=self.pg)
-            R, n = self.world, self.n
-            totals = self._rec_all[:, 0].contiguous()
-            cdf_all = self._rec_all[:, 1:1 + n].contiguous()
-            state_all = self._rec_all[:, 1 + n:].contiguous().view(torch.float32).view(R, 6, n)
+            totals, cdf_all, state_all = xch.gather_records()
+            xch.reduce_stats(self._stats)
         else:
             totals, cdf_all, state_all = total, cdf, st
         ops.resample(cdf_all, totals, self.n, self.id_offset, u, state_all, self._next, self.idx)
