@@ -52,17 +52,23 @@ struct EpiCfg {
   static_assert(kColsPerWarp % 32 == 0, "epilogue column split must be a multiple of 32");
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CTAS>
 struct GemmCfg {
+  // CTAS = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x BLOCK_N tile; each CTA
+  // stages its own 128 rows of A and HALF of the W tile, so shared-memory fill traffic from L2
+  // per SM drops by a third versus two independent 128 x BLOCK_N tiles.
+  static constexpr int kBRows = BLOCK_N / CTAS;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192 ? 4 : 5);
-  static constexpr int kTmemCols = (2 * BLOCK_N > 256) ? 512 : 256;
   static constexpr int kSlabBytes = 4096;  // per epilogue warp: 32 rows x 128 B transpose slab
   static constexpr int kEpiBytes = 8 * kSlabBytes;      // 8 x 4 KB (fp32) or 16 x 2 KB (bf16)
+  static constexpr int kStagesMax = (227 * 1024 - kEpiBytes - 1024 - 256) / kStageBytes;
+  static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
+  static constexpr int kTmemCols = (2 * BLOCK_N > 256) ? 512 : 256;
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(kStages >= 3, "pipeline too shallow");
 };
 
 // Exact (erf) GELU with erf by Abramowitz-Stegun 7.1.28: erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16,
@@ -182,15 +188,15 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
   __syncwarp();   // slab is rewritten by the next chunk
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, int CTAS>
 __global__ void __launch_bounds__((EpiCfg<BLOCK_N, MODE>::kThreads), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmArgs g) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, CTAS>;
   using Epi = EpiCfg<BLOCK_N, MODE>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
-  // 128-byte swizzle needs 1024-byte aligned tiles
+  // 128-byte swizzle needs 1024-byte aligned tiles (identical offsets in both CTAs of a pair)
   uint8_t* tiles = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* slabs = tiles + kStages * Cfg::kStageBytes;
@@ -201,58 +207,74 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_blocks = (g.M + kBlockM - 1) / kBlockM;
+  const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int m_blocks = (g.M + kBlockM * CTAS - 1) / (kBlockM * CTAS);   // per CTA group
   const int n_blocks = g.N / BLOCK_N;
   const int k_blocks = g.K / kBlockK;
   const int n_tiles = m_blocks * n_blocks;
+  const int group = blockIdx.x / CTAS, n_groups = gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], Epi::kWarps); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], Epi::kWarps * CTAS);   // epilogue warps of every CTA of the group
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_pair(tmem_ptr, Cfg::kTmemCols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_ptr, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA loads its own A rows / W half) ==========
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int tile = group; tile < n_tiles; tile += n_groups) {
         const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
+        const int a_row = (m_blk * CTAS + (int)cta_rank) * kBlockM;
+        const int b_row = n_blk * BLOCK_N + (int)cta_rank * Cfg::kBRows;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 0);
           uint8_t* sa = tiles + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, n_blk * BLOCK_N);
+          if (CTAS == 2) {
+            // bytes of both CTAs are counted on the leader's barrier (its MMA thread waits there)
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * 2);
+            const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_pair(sa, &tmA, bar, kb * kBlockK, a_row);
+            tma_load_2d_pair(sb, &tmB, bar, kb * kBlockK, b_row);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBlockK, a_row);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, b_row);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CTAS, BLOCK_N);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[as], aphase ^ 1, 1);   // epilogue has drained this accumulator
+        mbar_wait(&tmem_empty[as], aphase ^ 1, 1);   // epilogues have drained this accumulator
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase, 2);      // TMA bytes have landed
+          mbar_wait(&full_bar[stage], phase, 2);      // TMA bytes (of both CTAs) have landed
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
           const uint64_t adesc = make_smem_desc_k_sw128(sa);
@@ -260,13 +282,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (>>4) field
-            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                      (uint32_t)((kb | k) != 0));
+            if (CTAS == 2)
+              umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                             (uint32_t)((kb | k) != 0));
+            else
+              umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                        (uint32_t)((kb | k) != 0));
           }
-          umma_commit(&empty_bar[stage]);             // frees the smem stage when MMAs retire
+          // frees the smem stage (in both CTAs) when the MMAs retire
+          if (CTAS == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);                  // accumulator complete -> epilogue
+        // accumulator complete -> epilogues (of both CTAs)
+        if (CTAS == 2) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
       }
     }
   } else {
@@ -276,13 +304,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int kHalfCols = Epi::kColsPerWarp;
     constexpr int kSlab = (MODE <= 1) ? 2048 : 4096;
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
       const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_full[as], aphase, 3);
       tcgen05_fence_after();
-      const int row0 = m_blk * kBlockM + quarter * 32;
+      const int row0 = (m_blk * CTAS + (int)cta_rank) * kBlockM + quarter * 32;
       uint8_t* slab = slabs + (warp - 2) * kSlab;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                              (uint32_t)(as * BLOCK_N + half * kHalfCols);
@@ -295,15 +323,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));
+        else mbar_arrive(&tmem_empty[as]);
+      }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 

@@ -10,6 +10,7 @@
 
 #include <mutex>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -84,21 +85,51 @@ static int num_sms() {
   return g_num_sms;
 }
 
+// VPF_GEMM_CTAS=1 selects the single-CTA (cta_group::1) kernel; default is the CTA-pair kernel.
+static int gemm_ctas() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("VPF_GEMM_CTAS");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
+template <int BLOCK_N, int MODE, int CTAS>
+static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g,
+                         cudaStream_t s) {
+  using Cfg = GemmCfg<BLOCK_N, CTAS>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, MODE, CTAS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = ((g.M + kBlockM * CTAS - 1) / (kBlockM * CTAS)) * (g.N / BLOCK_N);
+  const int max_groups = num_sms() / CTAS;
+  const int groups = tiles < max_groups ? tiles : max_groups;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * CTAS);
+  cfg.blockDim = dim3(EpiCfg<BLOCK_N, MODE>::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VPF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g));
+  return VPF_OK;
+}
+
 template <int BLOCK_N, int MODE>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g,
                          cudaStream_t s) {
-  using Cfg = GemmCfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VPF_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N, MODE>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
-  const int tiles = ((g.M + kBlockM - 1) / kBlockM) * (g.N / BLOCK_N);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_kernel<BLOCK_N, MODE><<<grid, EpiCfg<BLOCK_N, MODE>::kThreads, Cfg::kSmemBytes, s>>>(tmA, tmB, g);
-  VPF_LAUNCH_CHECK();
-  return VPF_OK;
+  return gemm_ctas() == 2 ? launch_gemm_c<BLOCK_N, MODE, 2>(tmA, tmB, g, s)
+                          : launch_gemm_c<BLOCK_N, MODE, 1>(tmA, tmB, g, s);
 }
 
 template <int BLOCK_N>
@@ -264,7 +295,7 @@ int vpf_vit_set_weights(vpf_vit* h, const void* const* p, int n) {
   h->patch_w = p[k++]; h->patch_b = (const float*)p[k++];
   h->cls = (const float*)p[k++]; h->pos = (const float*)p[k++];
   int rc;
-  if ((rc = make_map(&h->m_patch, h->patch_w, D, 768, pick_block_n(D)))) return rc;
+  if ((rc = make_map(&h->m_patch, h->patch_w, D, 768, pick_block_n(D) / gemm_ctas()))) return rc;
   for (int l = 0; l < L; ++l) {
     LayerW& w = h->layers[l];
     w.ln1_g = (const float*)p[k++]; w.ln1_b = (const float*)p[k++];
@@ -273,10 +304,10 @@ int vpf_vit_set_weights(vpf_vit* h, const void* const* p, int n) {
     w.ln2_g = (const float*)p[k++]; w.ln2_b = (const float*)p[k++];
     w.fc1_w = p[k++]; w.fc1_b = (const float*)p[k++];
     w.fc2_w = p[k++]; w.fc2_b = (const float*)p[k++];
-    if ((rc = make_map(&w.m_qkv, w.qkv_w, 3 * D, D, pick_block_n(3 * D)))) return rc;
-    if ((rc = make_map(&w.m_proj, w.proj_w, D, D, pick_block_n(D)))) return rc;
-    if ((rc = make_map(&w.m_fc1, w.fc1_w, 4 * D, D, pick_block_n(4 * D)))) return rc;
-    if ((rc = make_map(&w.m_fc2, w.fc2_w, D, 4 * D, pick_block_n(D)))) return rc;
+    if ((rc = make_map(&w.m_qkv, w.qkv_w, 3 * D, D, pick_block_n(3 * D) / gemm_ctas()))) return rc;
+    if ((rc = make_map(&w.m_proj, w.proj_w, D, D, pick_block_n(D) / gemm_ctas()))) return rc;
+    if ((rc = make_map(&w.m_fc1, w.fc1_w, 4 * D, D, pick_block_n(4 * D) / gemm_ctas()))) return rc;
+    if ((rc = make_map(&w.m_fc2, w.fc2_w, D, 4 * D, pick_block_n(D) / gemm_ctas()))) return rc;
   }
   h->norm_g = (const float*)p[k++]; h->norm_b = (const float*)p[k++];
   h->has_weights = true;
@@ -378,7 +409,7 @@ int vpf_gemm_bf16(const void* A, const void* W, const float* bias, void* out, co
   CUtensorMap ma, mb;
   int rc;
   if ((rc = make_map(&ma, A, M, K, kBlockM))) return rc;
-  if ((rc = make_map(&mb, W, N, K, bn))) return rc;
+  if ((rc = make_map(&mb, W, N, K, bn / gemm_ctas()))) return rc;
   GemmArgs g{M, N, K, bias, out, pos};
   return launch_gemm(ma, mb, g, mode, (cudaStream_t)stream);
 }
