@@ -1,0 +1,335 @@
+// Fused multi-head self-attention for ViT/16 @224 on tcgen05 (T = 197 tokens, head dim 64).
+//
+// Persistent, one CTA per SM, looping over (crop, head) pairs.  A pair is two "units" (query
+// tiles of 128 rows: tokens 0-127 and 128-196); each unit owns one TMEM buffer and one softmax
+// warpgroup, so the tensor pipe works for one unit while the other unit's softmax runs:
+//
+//   warp 0      TMA producer: Q tile (128 x 64) per unit, K and V (208 x 64) per pair, from a
+//               3-D tensor map [crop][token][3D] so tokens >= 197 are zero-filled by the TMA
+//               unit itself; 128-byte swizzle; 4 Q stages / 2 KV stages.
+//   warp 1      MMA issuer (one thread):  S = Q K^T   tcgen05.mma M=128 N=208 K=16 x4 (SS)
+//                                         O = P V     tcgen05.mma M=128 N=64  K=16 x13 with P
+//               read straight from TMEM (TS form) and V as an MN-major shared-memory operand.
+//   warps 2-5   softmax warpgroup of tile 0 / TMEM buffer 0; warps 6-9 the same for tile 1:
+//               thread = query row; two tcgen05.ld passes over S (row max, then exp2 + row sum),
+//               P written back in place as packed bf16 with tcgen05.st; after O = P V the same
+//               threads normalise O by the row sum and store it through the (now free) Q stage,
+//               coalesced.
+//
+// TMEM (512 columns): buffer b at column 256 b:  S [0,208)  P aliases [0,104)  O [128,192).
+// qkv: bf16 [n_crops*197][3D] (timm's fused qkv layout), out: bf16 [n_crops*197][D].
+#pragma once
+
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace vpf {
+namespace attn {
+
+static constexpr int kT = 197;          // tokens
+static constexpr int kD = 64;           // head dim
+static constexpr int kKeys = 208;       // keys padded to a multiple of 16 (UMMA N / K granularity)
+static constexpr int kQStages = 4;
+static constexpr int kKVStages = 2;
+static constexpr int kQBytes = 128 * kD * 2;        // 16 KB
+static constexpr int kKVBytes = kKeys * kD * 2;     // 26 KB (1024-byte multiple)
+static constexpr int kThreads = 320;
+static constexpr int kSmemBytes = kQStages * kQBytes + kKVStages * 2 * kKVBytes + 1024 + 256;
+static constexpr int kTmemCols = 512;
+static constexpr int kBufCols = 256;
+static constexpr int kOCol = 128;
+
+// tcgen05.mma with the A operand in tensor memory (TS form)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// MN-major operand ([k][64 contiguous n] rows of 128 B, 128-byte swizzle, 8-row atoms 1024 B apart)
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                 // LBO: unused (a single 64-element group along N)
+  d |= (uint64_t)(1024 >> 4) << 32;       // SBO: next group of 8 k-rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(int M, int N) {
+  return make_idesc_bf16(M, N) | (1u << 16);     // B operand MN-major
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
+        "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+        "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]),
+        "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+        "r"(v[7])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    __nv_bfloat16* __restrict__ out, int n_pairs, int heads, int D) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = base;                                   // [kQStages][128][128 B]
+  uint8_t* sK = sQ + kQStages * kQBytes;                // [kKVStages][208][128 B]
+  uint8_t* sV = sK + kKVStages * kKVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKVStages * kKVBytes);
+  uint64_t* q_full = bars;            // [4]
+  uint64_t* q_empty = bars + 4;       // [4]
+  uint64_t* kv_full = bars + 8;       // [2]
+  uint64_t* kv_empty = bars + 10;     // [2]
+  uint64_t* s_full = bars + 12;       // [2] per TMEM buffer
+  uint64_t* p_full = bars + 14;       // [2]
+  uint64_t* o_full = bars + 16;       // [2]
+  uint64_t* buf_empty = bars + 18;    // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_pairs = (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    for (int i = 0; i < kQStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 4); }
+    for (int i = 0; i < kKVStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1); mbar_init(&buf_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, kTmemCols); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int ip = 0; ip < my_pairs; ++ip) {
+        const int pair = (int)blockIdx.x + ip * (int)gridDim.x;
+        const int crop = pair / heads, head = pair - crop * heads;
+        const int ks = ip & 1;
+        mbar_wait(&kv_empty[ks], ((ip >> 1) & 1) ^ 1, 10);
+        mbar_arrive_expect_tx(&kv_full[ks], 2 * kKVBytes);
+        tma_load_3d(sK + ks * kKVBytes, &tmKV, &kv_full[ks], D + head * kD, 0, crop);
+        tma_load_3d(sV + ks * kKVBytes, &tmKV, &kv_full[ks], 2 * D + head * kD, 0, crop);
+        for (int t = 0; t < 2; ++t) {
+          const int u = 2 * ip + t, qs = u & 3;
+          mbar_wait(&q_empty[qs], ((u >> 2) & 1) ^ 1, 11);
+          mbar_arrive_expect_tx(&q_full[qs], kQBytes);
+          tma_load_3d(sQ + qs * kQBytes, &tmQ, &q_full[qs], head * kD, t * 128, crop);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, kKeys);
+      constexpr uint32_t idesc_o = make_idesc_bf16_bmn(128, kD);
+      const int units = 2 * my_pairs;
+      auto issue_s = [&](int u) {
+        const int ip = u >> 1, b = u & 1, qs = u & 3, ks = ip & 1;
+        mbar_wait(&q_full[qs], (u >> 2) & 1, 12);
+        if (b == 0) mbar_wait(&kv_full[ks], (ip >> 1) & 1, 13);
+        mbar_wait(&buf_empty[b], (ip & 1) ^ 1, 14);
+        tcgen05_fence_after();
+        const uint64_t adesc = make_smem_desc_k_sw128(smem_u32(sQ + qs * kQBytes));
+        const uint64_t bdesc = make_smem_desc_k_sw128(smem_u32(sK + ks * kKVBytes));
+        const uint32_t d = tmem_base + (uint32_t)(b * kBufCols);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_bf16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_s, (uint32_t)(k != 0));
+        umma_commit(&s_full[b]);
+      };
+      auto issue_pv = [&](int u) {
+        const int ip = u >> 1, b = u & 1, ks = ip & 1;
+        mbar_wait(&p_full[b], ip & 1, 15);
+        tcgen05_fence_after();
+        const uint32_t vaddr = smem_u32(sV + ks * kKVBytes);
+        const uint32_t p = tmem_base + (uint32_t)(b * kBufCols);
+        const uint32_t d = p + (uint32_t)kOCol;
+#pragma unroll
+        for (int k = 0; k < kKeys / 16; ++k)      // 16 keys: 8 packed P columns, 2 V row atoms
+          umma_bf16_ts(d, p + (uint32_t)(k * 8), make_smem_desc_mn_sw128(vaddr + k * 2048), idesc_o,
+                       (uint32_t)(k != 0));
+        umma_commit(&o_full[b]);
+        if (b == 1) umma_commit(&kv_empty[ks]);   // every MMA of this pair has retired
+      };
+      if (units > 0) { issue_s(0); issue_s(1); }
+      for (int u = 0; u < units; ++u) {
+        issue_pv(u);
+        if (u + 2 < units) issue_s(u + 2);
+      }
+    }
+  } else {
+    // ===================== softmax / output warpgroups =====================
+    const int b = (warp - 2) >> 2;                 // tile index == TMEM buffer
+    const int quarter = warp & 3;                  // TMEM lane quarter
+    const int row = quarter * 32 + lane;           // row inside the 128-row tile
+    const int token = b * 128 + row;
+    const bool warp_has_rows = (b * 128 + quarter * 32) < kT;
+    const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    const uint32_t tbuf = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * kBufCols);
+    for (int ip = 0; ip < my_pairs; ++ip) {
+      const int pair = (int)blockIdx.x + ip * (int)gridDim.x;
+      const int crop = pair / heads, head = pair - crop * heads;
+      const int u = 2 * ip + b, qs = u & 3;
+      mbar_wait(&s_full[b], ip & 1, 16);
+      tcgen05_fence_after();
+      float inv_l = 0.f;
+      if (warp_has_rows) {
+        uint32_t v[32];
+        // pass 1: row maximum over the 197 real keys
+        float m = -INFINITY;
+#pragma unroll 1
+        for (int ch = 0; ch < 6; ++ch) {
+          tmem_ld_32x32(tbuf + (uint32_t)(ch * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+        tmem_ld_32x16(tbuf + 192u, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < kT - 192; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+        const float mc = m * c;
+        // pass 2: p = 2^(s c - m c), row sum, P (bf16 pairs) written in place over S
+        float l = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < 6; ++ch) {
+          tmem_ld_32x32(tbuf + (uint32_t)(ch * 32), v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float p0 = ex2(fmaf(__uint_as_float(v[2 * j]), c, -mc));
+            const float p1 = ex2(fmaf(__uint_as_float(v[2 * j + 1]), c, -mc));
+            l += p0 + p1;
+            pk[j] = pack2(p0, p1);
+          }
+          tmem_st_32x16(tbuf + (uint32_t)(ch * 16), pk);
+        }
+        {
+          tmem_ld_32x16(tbuf + 192u, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k0 = 192 + 2 * j;
+            const float p0 = (k0 < kT) ? ex2(fmaf(__uint_as_float(v[2 * j]), c, -mc)) : 0.f;
+            const float p1 = (k0 + 1 < kT) ? ex2(fmaf(__uint_as_float(v[2 * j + 1]), c, -mc)) : 0.f;
+            l += p0 + p1;
+            pk[j] = pack2(p0, p1);
+          }
+          tmem_st_32x8(tbuf + 96u, pk);
+        }
+        tmem_st_wait();
+        inv_l = 1.0f / l;
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);
+      // ---- O = P V is ready: normalise, stage through this unit's Q tile, store coalesced ----
+      mbar_wait(&o_full[b], ip & 1, 17);
+      tcgen05_fence_after();
+      uint8_t* stage = sQ + qs * kQBytes + quarter * 32 * 128;     // this warp's 32 rows
+      if (warp_has_rows) {
+        uint32_t v[32];
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          tmem_ld_32x32(tbuf + (uint32_t)(kOCol + hlf * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack2(__uint_as_float(v[q * 8 + 0]) * inv_l, __uint_as_float(v[q * 8 + 1]) * inv_l);
+            o.y = pack2(__uint_as_float(v[q * 8 + 2]) * inv_l, __uint_as_float(v[q * 8 + 3]) * inv_l);
+            o.z = pack2(__uint_as_float(v[q * 8 + 4]) * inv_l, __uint_as_float(v[q * 8 + 5]) * inv_l);
+            o.w = pack2(__uint_as_float(v[q * 8 + 6]) * inv_l, __uint_as_float(v[q * 8 + 7]) * inv_l);
+            const int chunk = hlf * 4 + q;
+            *reinterpret_cast<uint4*>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&buf_empty[b]);     // TMEM buffer may take the next unit's S
+      if (warp_has_rows) {
+        __nv_bfloat16* orow = out + ((size_t)crop * kT + (size_t)(b * 128 + quarter * 32)) * D + head * kD;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3), chunk = lane & 7;
+          if (b * 128 + quarter * 32 + r < kT) {
+            const uint4 val = *reinterpret_cast<const uint4*>(stage + r * 128 + ((chunk ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(orow + (size_t)r * D + chunk * 8) = val;
+          }
+        }
+      }
+      // generic-proxy accesses of the stage are ordered before the TMA (async proxy) refill
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_empty[qs]);       // Q stage may be refilled
+      (void)token;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace attn
+}  // namespace vpf

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 
 #include <mutex>
 #include <stdarg.h>
@@ -72,6 +73,21 @@ static int pick_block_n(int N) {
   if (N % 192 == 0) return 192;
   if (N % 128 == 0) return 128;
   return 0;
+}
+
+// 3-D view [crop][token][3D] of the fused qkv buffer: the TMA unit zero-fills tokens >= 197.
+static int make_qkv_map(CUtensorMap* map, const void* ptr, int n_crops, int D, uint32_t box_tokens) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return VPF_ERR_CUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)3 * D, (cuuint64_t)kTokens, (cuuint64_t)n_crops};
+  cuuint64_t strides[2] = {(cuuint64_t)3 * D * 2, (cuuint64_t)kTokens * 3 * D * 2};
+  cuuint32_t box[3] = {64, box_tokens, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(qkv) failed: %d", (int)r); return VPF_ERR_CUDA; }
+  return VPF_OK;
 }
 
 static int g_num_sms = 0;
@@ -222,6 +238,43 @@ __global__ void cls_init_kernel(float* __restrict__ X, const float* __restrict__
   X[(size_t)crop * kTokens * D + d] = cls[d] + pos[d];
 }
 
+// VPF_ATTN=mma selects the warp-level mma.sync kernel; default is the tcgen05 kernel.
+static bool attn_use_tc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VPF_ATTN");
+    v = (e && e[0] == 'm') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_crops, int heads,
+                            const CUtensorMap* mq, const CUtensorMap* mkv, cudaStream_t s) {
+  const int D = heads * kHeadDim;
+  if (attn_use_tc()) {
+    static bool attr = false;
+    if (!attr) {
+      VPF_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, attn::kSmemBytes));
+      attr = true;
+    }
+    const int n_pairs = n_crops * heads;
+    const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
+    attn::attention_tc_kernel<<<grid, attn::kThreads, attn::kSmemBytes, s>>>(*mq, *mkv, out, n_pairs,
+                                                                             heads, D);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      VPF_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kAttnSmem));
+      attr = true;
+    }
+    attention_kernel<<<dim3(heads, n_crops), kAttnThreads, kAttnSmem, s>>>(qkv, out, D);
+  }
+  VPF_LAUNCH_CHECK();
+  return VPF_OK;
+}
+
 struct LayerW {
   const float *ln1_g, *ln1_b, *qkv_b, *proj_b, *ln2_g, *ln2_b, *fc1_b, *fc2_b;
   const void *qkv_w, *proj_w, *fc1_w, *fc2_w;
@@ -247,7 +300,7 @@ struct vpf_vit {
   // activation tensor maps, cached for the last n_crops
   int maps_for = -1;
   const void* maps_patches = nullptr;
-  CUtensorMap a_patches, a_xn, a_big;
+  CUtensorMap a_patches, a_xn, a_big, a_q, a_kv;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -350,14 +403,10 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
     if ((rc = make_map(&h->a_patches, patches, M0, 768, kBlockM))) return rc;
     if ((rc = make_map(&h->a_xn, h->Xn, M, D, kBlockM))) return rc;
     if ((rc = make_map(&h->a_big, h->big, M, 4 * D, kBlockM))) return rc;
+    if ((rc = make_qkv_map(&h->a_q, h->big, n, D, 128))) return rc;
+    if ((rc = make_qkv_map(&h->a_kv, h->big, n, D, attn::kKeys))) return rc;
     h->maps_for = n;
     h->maps_patches = patches;
-  }
-  static bool attn_attr = false;
-  if (!attn_attr) {
-    VPF_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kAttnSmem));
-    attn_attr = true;
   }
   const int ln_blocks = (M + 7) / 8;
 
@@ -375,8 +424,7 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
       GemmArgs g{M, 3 * D, D, w.qkv_b, h->big, nullptr};
       if ((rc = launch_gemm(h->a_xn, w.m_qkv, g, kBiasBf16, s))) return rc;
     }
-    attention_kernel<<<dim3(H, n), kAttnThreads, kAttnSmem, s>>>(h->big, h->Xn, D);
-    VPF_LAUNCH_CHECK();
+    if ((rc = launch_attention(h->big, h->Xn, n, H, &h->a_q, &h->a_kv, s))) return rc;
     {
       GemmArgs g{M, D, D, w.proj_b, h->X, nullptr};
       if ((rc = launch_gemm(h->a_xn, w.m_proj, g, kBiasResidualF32, s))) return rc;
@@ -426,12 +474,12 @@ int vpf_layernorm(const float* x, const float* gamma, const float* beta, void* o
 
 int vpf_attention(const void* qkv, void* out, int n_crops, int heads, void* stream) {
   VPF_REQUIRE(qkv && out && n_crops > 0 && heads > 0, "vpf_attention: bad arguments");
-  VPF_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                kAttnSmem));
-  attention_kernel<<<dim3(heads, n_crops), kAttnThreads, kAttnSmem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, heads * kHeadDim);
-  VPF_LAUNCH_CHECK();
-  return VPF_OK;
+  CUtensorMap mq, mkv;
+  int rc;
+  if ((rc = make_qkv_map(&mq, qkv, n_crops, heads * kHeadDim, 128))) return rc;
+  if ((rc = make_qkv_map(&mkv, qkv, n_crops, heads * kHeadDim, attn::kKeys))) return rc;
+  return launch_attention((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n_crops, heads, &mq, &mkv,
+                          (cudaStream_t)stream);
 }
 
 }  // extern "C"
