@@ -43,7 +43,7 @@ def test_host_only_entry_points():
     bad = _lib.VitConfig(100, 12, 12, 16)
     assert lib.vpf_vit_create(C.byref(h), C.byref(bad)) == -1
     assert lib.vpf_vit_create(C.byref(h), C.byref(cfg)) == 0 and h.value
-    assert lib.vpf_vit_launches(h) == 2 + 7 * 12 + 1
+    assert lib.vpf_vit_launches(h) == 2 + 7 * 11 + 10        # CLS-only last block
     assert lib.vpf_vit_forward(h, 1, 1, 1, None) == -3          # weights / workspace missing
     assert lib.vpf_vit_destroy(h) == 0
 

@@ -125,3 +125,23 @@ def test_vit_forward_matches_oracle(model, n):
     # a smaller batch through the same handle gives bit-identical rows (batch invariance)
     got2 = enc.forward(patches[:196 * 2].contiguous(), 2).cpu()
     assert torch.equal(got2, got[:2])
+
+
+def test_cls_only_last_block_matches_full_last_block(monkeypatch):
+    """The CLS-only last block is exact pruning: same embedding as running the last block on
+    every token (up to the bf16 rounding of the one attention row computed by another kernel)."""
+    from vitparticlefiltertracker_b200 import ops, pack_for_device
+    dev = cuda()
+    model, n = "vit_tiny_patch16_224", 5
+    cfg = VIT_CONFIGS[model]
+    sd = init_vit_weights(model)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    patches = torch.randn(n * 196, 768, generator=g).to(torch.bfloat16).to(dev)
+    packed = pack_for_device(model, sd)
+    pruned = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], n, packed, dev)
+    a = pruned.forward(patches, n).cpu()
+    monkeypatch.setenv("VPF_CLS_PRUNE", "0")
+    full = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], n, packed, dev)
+    assert full.launches == 2 + 7 * 12 + 1 and pruned.launches == 2 + 7 * 11 + 10
+    b = full.forward(patches, n).cpu()
+    assert _rel(a, b) < 2e-3, _rel(a, b)

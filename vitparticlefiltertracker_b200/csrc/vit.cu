@@ -50,15 +50,16 @@ static EncodeTiledFn encode_fn() {
 
 // bf16 row-major [rows][cols] matrix, tile = box_rows x 64 columns, 128-byte swizzle
 static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols,
-                    uint32_t box_rows) {
+                    uint32_t box_rows, uint64_t pitch_elems = 0) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return VPF_ERR_CUDA; }
-  if (((uintptr_t)ptr & 15) || (cols * 2) % 16) {
+  if (!pitch_elems) pitch_elems = cols;
+  if (((uintptr_t)ptr & 15) || (pitch_elems * 2) % 16) {
     set_error("TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
     return VPF_ERR_INVALID;
   }
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
+  cuuint64_t strides[1] = {pitch_elems * 2};
   cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
@@ -76,11 +77,12 @@ static int pick_block_n(int N) {
 }
 
 // 3-D view [crop][token][3D] of the fused qkv buffer: the TMA unit zero-fills tokens >= 197.
-static int make_qkv_map(CUtensorMap* map, const void* ptr, int n_crops, int D, uint32_t box_tokens) {
+static int make_qkv_map(CUtensorMap* map, const void* ptr, int n_crops, int D, uint32_t box_tokens,
+                        int ncols3 = 3) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return VPF_ERR_CUDA; }
-  cuuint64_t dims[3] = {(cuuint64_t)3 * D, (cuuint64_t)kTokens, (cuuint64_t)n_crops};
-  cuuint64_t strides[2] = {(cuuint64_t)3 * D * 2, (cuuint64_t)kTokens * 3 * D * 2};
+  cuuint64_t dims[3] = {(cuuint64_t)ncols3 * D, (cuuint64_t)kTokens, (cuuint64_t)n_crops};
+  cuuint64_t strides[2] = {(cuuint64_t)ncols3 * D * 2, (cuuint64_t)kTokens * ncols3 * D * 2};
   cuuint32_t box[3] = {64, box_tokens, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides,
@@ -275,6 +277,99 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_
   return VPF_OK;
 }
 
+// ---- CLS-only last block (exact: the encoder output is the CLS row, and in the last block a
+// token's output depends on the other tokens only through their keys and values) --------------
+// Xc[crop][:] = X[crop*197][:]
+__global__ void gather_cls_kernel(const float* __restrict__ X, float* __restrict__ Xc, int n_crops,
+                                  int D) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;     // float4 index
+  const int nv = D >> 2;
+  if (i >= n_crops * nv) return;
+  int crop = i / nv, v = i - crop * nv;
+  reinterpret_cast<float4*>(Xc)[i] =
+      reinterpret_cast<const float4*>(X + (size_t)crop * kTokens * D)[v];
+}
+
+// One warp per (crop, head): o = softmax(q K^T / 8) V for the single CLS query.
+// q: bf16 [n_crops][D]; kv: bf16 [n_crops*197][2D] (K then V); o: bf16 [n_crops][D].
+__global__ void __launch_bounds__(256) cls_attention_kernel(const __nv_bfloat16* __restrict__ q,
+                                                            const __nv_bfloat16* __restrict__ kv,
+                                                            __nv_bfloat16* __restrict__ o,
+                                                            int n_pairs, int heads) {
+  const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pair >= n_pairs) return;
+  const int crop = pair / heads, head = pair - crop * heads;
+  const int D = heads * kHeadDim;
+  float qf[kHeadDim];
+  {
+    const uint4* q4 = reinterpret_cast<const uint4*>(q + (size_t)crop * D + head * kHeadDim);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint4 t = __ldg(q4 + i);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(h[j]);
+        qf[i * 8 + j * 2] = f.x; qf[i * 8 + j * 2 + 1] = f.y;
+      }
+    }
+  }
+  const __nv_bfloat16* kbase = kv + (size_t)crop * kTokens * 2 * D + head * kHeadDim;
+  const float c = 0.125f * 1.4426950408889634f;
+  float sc[7];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const int j = i * 32 + lane;
+    float acc = -INFINITY;
+    if (j < kTokens) {
+      const uint4* k4 = reinterpret_cast<const uint4*>(kbase + (size_t)j * 2 * D);
+      acc = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        uint4 t = __ldg(k4 + u);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          float2 f = __bfloat1622float2(h[w]);
+          acc = fmaf(qf[u * 8 + w * 2], f.x, acc);
+          acc = fmaf(qf[u * 8 + w * 2 + 1], f.y, acc);
+        }
+      }
+      acc *= c;
+    }
+    sc[i] = acc;
+    m = fmaxf(m, acc);
+  }
+  m = warp_max(m);
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    sc[i] = exp2f(sc[i] - m);          // exp2(-inf) = 0 for the padded keys
+    l += sc[i];
+  }
+  l = warp_sum(l);
+  const __nv_bfloat16* vbase = kbase + D + 2 * lane;
+  float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+#pragma unroll 8
+    for (int jj = 0; jj < 32; ++jj) {
+      const int j = i * 32 + jj;
+      const float p = __shfl_sync(0xffffffffu, sc[i], jj);
+      if (j < kTokens) {
+        float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vbase + (size_t)j * 2 * D));
+        o0 = fmaf(p, f.x, o0);
+        o1 = fmaf(p, f.y, o1);
+      }
+    }
+  }
+  const float inv = 1.0f / l;
+  *reinterpret_cast<__nv_bfloat162*>(o + (size_t)crop * D + head * kHeadDim + 2 * lane) =
+      __floats2bfloat162_rn(o0 * inv, o1 * inv);
+}
+
 struct LayerW {
   const float *ln1_g, *ln1_b, *qkv_b, *proj_b, *ln2_g, *ln2_b, *fc1_b, *fc2_b;
   const void *qkv_w, *proj_w, *fc1_w, *fc2_w;
@@ -301,6 +396,9 @@ struct vpf_vit {
   int maps_for = -1;
   const void* maps_patches = nullptr;
   CUtensorMap a_patches, a_xn, a_big, a_q, a_kv;
+  // CLS-only last block: strided CLS rows of Xn, compact [n][D] / [n][4D] operands
+  CUtensorMap a_xn_cls, a_ocls, a_xnc, a_hc, m_kv_last, m_q_last;
+  bool cls_prune = true;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -322,6 +420,10 @@ int vpf_vit_create(vpf_vit** out, const vpf_vit_config* cfg) {
   vpf_vit* h = new vpf_vit();
   h->cfg = *cfg;
   h->layers.resize(cfg->depth);
+  {
+    const char* e = getenv("VPF_CLS_PRUNE");    // VPF_CLS_PRUNE=0: run the last block on all rows
+    h->cls_prune = !(e && e[0] == '0');
+  }
   *out = h;
   return VPF_OK;
 }
@@ -363,6 +465,13 @@ int vpf_vit_set_weights(vpf_vit* h, const void* const* p, int n) {
     if ((rc = make_map(&w.m_fc2, w.fc2_w, D, 4 * D, pick_block_n(D) / gemm_ctas()))) return rc;
   }
   h->norm_g = (const float*)p[k++]; h->norm_b = (const float*)p[k++];
+  {  // last block, CLS-only path: separate views of the fused qkv weight (Q rows, then K|V rows)
+    const LayerW& w = h->layers[L - 1];
+    const __nv_bfloat16* qkv = (const __nv_bfloat16*)w.qkv_w;
+    if ((rc = make_map(&h->m_q_last, qkv, D, D, pick_block_n(D) / gemm_ctas()))) return rc;
+    if ((rc = make_map(&h->m_kv_last, qkv + (size_t)D * D, 2 * D, D,
+                       pick_block_n(2 * D) / gemm_ctas()))) return rc;
+  }
   h->has_weights = true;
   return VPF_OK;
 }
@@ -384,7 +493,93 @@ int vpf_vit_set_workspace(vpf_vit* h, void* ws, size_t bytes) {
 
 int vpf_vit_launches(const vpf_vit* h) {
   if (!h) return 0;
-  return 2 /*cls, patch embed*/ + 7 * h->cfg.depth + 1 /*final LN*/;
+  const int L = h->cfg.depth;
+  if (!h->cls_prune) return 2 /*cls, patch embed*/ + 7 * L + 1 /*final LN*/;
+  return 2 + 7 * (L - 1) + 10;
+}
+
+// One full encoder block on every token row.
+static int run_block(vpf_vit* h, const LayerW& w, int n, cudaStream_t s) {
+  const int D = h->cfg.dim, H = h->cfg.heads, M = n * kTokens;
+  const int ln_blocks = (M + 7) / 8;
+  int rc;
+  layernorm_kernel<__nv_bfloat16><<<ln_blocks, 256, 0, s>>>(h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D);
+  VPF_LAUNCH_CHECK();
+  {
+    GemmArgs g{M, 3 * D, D, w.qkv_b, h->big, nullptr};
+    if ((rc = launch_gemm(h->a_xn, w.m_qkv, g, kBiasBf16, s))) return rc;
+  }
+  if ((rc = launch_attention(h->big, h->Xn, n, H, &h->a_q, &h->a_kv, s))) return rc;
+  {
+    GemmArgs g{M, D, D, w.proj_b, h->X, nullptr};
+    if ((rc = launch_gemm(h->a_xn, w.m_proj, g, kBiasResidualF32, s))) return rc;
+  }
+  layernorm_kernel<__nv_bfloat16><<<ln_blocks, 256, 0, s>>>(h->X, D, w.ln2_g, w.ln2_b, h->Xn, M, D);
+  VPF_LAUNCH_CHECK();
+  {
+    GemmArgs g{M, 4 * D, D, w.fc1_b, h->big, nullptr};
+    if ((rc = launch_gemm(h->a_xn, w.m_fc1, g, kBiasGeluBf16, s))) return rc;
+  }
+  {
+    GemmArgs g{M, D, 4 * D, w.fc2_b, h->X, nullptr};
+    if ((rc = launch_gemm(h->a_big, w.m_fc2, g, kBiasResidualF32, s))) return rc;
+  }
+  return VPF_OK;
+}
+
+// Last block, CLS rows only (exact): keys / values for every token, everything else for the n
+// CLS rows.  Compact operands live in the unused upper part of `big`.
+struct ClsBufs {
+  __nv_bfloat16 *q, *o, *xn, *hc;
+  float* xc;
+};
+static ClsBufs cls_bufs(const vpf_vit* h, int n) {
+  const size_t D = h->cfg.dim, M = (size_t)n * kTokens;
+  uint8_t* b = reinterpret_cast<uint8_t*>(h->big) + align_up(M * 2 * D * 2, 256);
+  ClsBufs c;
+  c.q = (__nv_bfloat16*)b;  b += align_up((size_t)n * D * 2, 256);
+  c.o = (__nv_bfloat16*)b;  b += align_up((size_t)n * D * 2, 256);
+  c.xn = (__nv_bfloat16*)b; b += align_up((size_t)n * D * 2, 256);
+  c.hc = (__nv_bfloat16*)b; b += align_up((size_t)n * 4 * D * 2, 256);
+  c.xc = (float*)b;
+  return c;
+}
+
+static int run_last_block_cls(vpf_vit* h, const LayerW& w, int n, float* emb, cudaStream_t s) {
+  const int D = h->cfg.dim, H = h->cfg.heads, M = n * kTokens;
+  const ClsBufs c = cls_bufs(h, n);
+  int rc;
+  layernorm_kernel<__nv_bfloat16><<<(M + 7) / 8, 256, 0, s>>>(h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D);
+  VPF_LAUNCH_CHECK();
+  {  // K, V for every token: rows [D, 3D) of the fused qkv weight
+    GemmArgs g{M, 2 * D, D, w.qkv_b + D, h->big, nullptr};
+    if ((rc = launch_gemm(h->a_xn, h->m_kv_last, g, kBiasBf16, s))) return rc;
+  }
+  {  // Q for the CLS rows only (strided view of Xn)
+    GemmArgs g{n, D, D, w.qkv_b, c.q, nullptr};
+    if ((rc = launch_gemm(h->a_xn_cls, h->m_q_last, g, kBiasBf16, s))) return rc;
+  }
+  cls_attention_kernel<<<(n * H + 7) / 8, 256, 0, s>>>(c.q, h->big, c.o, n * H, H);
+  VPF_LAUNCH_CHECK();
+  gather_cls_kernel<<<(n * (D / 4) + 255) / 256, 256, 0, s>>>(h->X, c.xc, n, D);
+  VPF_LAUNCH_CHECK();
+  {
+    GemmArgs g{n, D, D, w.proj_b, c.xc, nullptr};
+    if ((rc = launch_gemm(h->a_ocls, w.m_proj, g, kBiasResidualF32, s))) return rc;
+  }
+  layernorm_kernel<__nv_bfloat16><<<(n + 7) / 8, 256, 0, s>>>(c.xc, D, w.ln2_g, w.ln2_b, c.xn, n, D);
+  VPF_LAUNCH_CHECK();
+  {
+    GemmArgs g{n, 4 * D, D, w.fc1_b, c.hc, nullptr};
+    if ((rc = launch_gemm(h->a_xnc, w.m_fc1, g, kBiasGeluBf16, s))) return rc;
+  }
+  {
+    GemmArgs g{n, D, 4 * D, w.fc2_b, c.xc, nullptr};
+    if ((rc = launch_gemm(h->a_hc, w.m_fc2, g, kBiasResidualF32, s))) return rc;
+  }
+  layernorm_kernel<float><<<(n + 7) / 8, 256, 0, s>>>(c.xc, D, h->norm_g, h->norm_b, emb, n, D);
+  VPF_LAUNCH_CHECK();
+  return VPF_OK;
 }
 
 int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* stream) {
@@ -396,7 +591,7 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
   VPF_REQUIRE(n > 0 && n <= h->cfg.max_crops, "vpf_vit_forward: n_crops %d outside [1, %d]", n,
               h->cfg.max_crops);
   cudaStream_t s = (cudaStream_t)stream;
-  const int D = h->cfg.dim, L = h->cfg.depth, H = h->cfg.heads;
+  const int D = h->cfg.dim, L = h->cfg.depth;
   const int M0 = n * 196, M = n * kTokens;
   int rc;
   if (h->maps_for != n || h->maps_patches != patches) {
@@ -405,10 +600,14 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
     if ((rc = make_map(&h->a_big, h->big, M, 4 * D, kBlockM))) return rc;
     if ((rc = make_qkv_map(&h->a_q, h->big, n, D, 128))) return rc;
     if ((rc = make_qkv_map(&h->a_kv, h->big, n, D, attn::kKeys))) return rc;
+    const ClsBufs c = cls_bufs(h, n);
+    if ((rc = make_map(&h->a_xn_cls, h->Xn, n, D, kBlockM, (uint64_t)kTokens * D))) return rc;
+    if ((rc = make_map(&h->a_ocls, c.o, n, D, kBlockM))) return rc;
+    if ((rc = make_map(&h->a_xnc, c.xn, n, D, kBlockM))) return rc;
+    if ((rc = make_map(&h->a_hc, c.hc, n, 4 * D, kBlockM))) return rc;
     h->maps_for = n;
     h->maps_patches = patches;
   }
-  const int ln_blocks = (M + 7) / 8;
 
   cls_init_kernel<<<(n * D + 255) / 256, 256, 0, s>>>(h->X, h->cls, h->pos, n, D);
   VPF_LAUNCH_CHECK();
@@ -416,30 +615,10 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
     GemmArgs g{M0, D, 768, h->patch_b, h->X, h->pos};
     if ((rc = launch_gemm(h->a_patches, h->m_patch, g, kPatchEmbedF32, s))) return rc;
   }
-  for (int l = 0; l < L; ++l) {
-    const LayerW& w = h->layers[l];
-    layernorm_kernel<__nv_bfloat16><<<ln_blocks, 256, 0, s>>>(h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D);
-    VPF_LAUNCH_CHECK();
-    {
-      GemmArgs g{M, 3 * D, D, w.qkv_b, h->big, nullptr};
-      if ((rc = launch_gemm(h->a_xn, w.m_qkv, g, kBiasBf16, s))) return rc;
-    }
-    if ((rc = launch_attention(h->big, h->Xn, n, H, &h->a_q, &h->a_kv, s))) return rc;
-    {
-      GemmArgs g{M, D, D, w.proj_b, h->X, nullptr};
-      if ((rc = launch_gemm(h->a_xn, w.m_proj, g, kBiasResidualF32, s))) return rc;
-    }
-    layernorm_kernel<__nv_bfloat16><<<ln_blocks, 256, 0, s>>>(h->X, D, w.ln2_g, w.ln2_b, h->Xn, M, D);
-    VPF_LAUNCH_CHECK();
-    {
-      GemmArgs g{M, 4 * D, D, w.fc1_b, h->big, nullptr};
-      if ((rc = launch_gemm(h->a_xn, w.m_fc1, g, kBiasGeluBf16, s))) return rc;
-    }
-    {
-      GemmArgs g{M, D, 4 * D, w.fc2_b, h->X, nullptr};
-      if ((rc = launch_gemm(h->a_big, w.m_fc2, g, kBiasResidualF32, s))) return rc;
-    }
-  }
+  const int full_blocks = h->cls_prune ? L - 1 : L;
+  for (int l = 0; l < full_blocks; ++l)
+    if ((rc = run_block(h, h->layers[l], n, s))) return rc;
+  if (h->cls_prune) return run_last_block_cls(h, h->layers[L - 1], n, emb, s);
   layernorm_kernel<float><<<(n + 7) / 8, 256, 0, s>>>(h->X, (size_t)kTokens * D, h->norm_g,
                                                      h->norm_b, emb, n, D);
   VPF_LAUNCH_CHECK();
