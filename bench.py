@@ -199,10 +199,54 @@ def gemm_roofline(dev, M, D, peaks, reps=2):
                   "tflops": d["flops"] / float(np.mean(d["ms"])) / 1e9} for k, d in per.items()}
     achieved = tot_fl / tot_ms / 1e9
     peak = peaks["tflops_sustained"]
-    return {"bound": "tensor", "kernel": "gemm_bf16_kernel<tcgen05> (qkv+proj+fc1+fc2 of one block)",
+    traffic, traffic_src = None, None
+    prof = os.path.join(ROOT, "profiles", "ncu_gemm_r01.json")
+    if os.path.exists(prof) and M == 4096 * 197 and D == 768:     # captured on this exact shape
+        pj = json.load(open(prof))
+        traffic = pj["gemm_family_traffic_bytes_per_block"]
+        traffic_src = ("profiles/ncu_gemm_r01.json: dram__bytes_read+write summed over the four "
+                       "launches of one block (ncu --set full); algorithmic bytes "
+                       f"{pj['gemm_family_algorithmic_bytes_per_block']:.4g}")
+    return {"bound": "tensor", "kernel": "gemm_bf16_kernel<tcgen05, cta_group::2> (qkv+proj+fc1+fc2 of one block)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "peak_source": peaks["source"] + ", sustained bf16", "traffic": None,
+            "peak_source": peaks["source"] + ", sustained bf16", "traffic": traffic,
+            "traffic_source": traffic_src,
             "flops_per_launch_set": tot_fl, "ms_per_launch_set": tot_ms, "detail": detail}, tot_ms
+
+
+def hbm_kernels(dev, trk, frame, peaks, iters=10):
+    """K1 (crop) and K3/K4 (particle update + resampling) timed alone with CUDA events: achieved
+    HBM GB/s on their algorithmic bytes against the measured copy peak."""
+    from vitparticlefiltertracker_b200 import ops
+    out = {}
+    n = trk.n
+
+    def t(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / iters
+
+    ms = t(lambda: ops.crop_state(frame, trk.particles, trk.w0, trk.h0, trk.patches))
+    gbs = n * 301056 / ms / 1e6
+    out["crop_resize_patchify"] = {"ms": ms, "bytes": n * 301056, "GB/s": gbs,
+                                   "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
+    xch = trk.xch
+    total, cdf, _ = xch.local_views()
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    nxt = torch.empty_like(trk.particles)
+    ms = t(lambda: ops.resample(cdf.view(1, -1), total, n, 0, 0.37, trk.particles, nxt, idx))
+    gbs = n * 64 / ms / 1e6
+    out["resample_gather"] = {"ms": ms, "bytes": n * 64, "GB/s": gbs,
+                              "frac_of_hbm_peak": gbs / peaks["hbm_gbs"],
+                              "note": "latency-bound: 262 KB of traffic"}
+    return out
 
 
 def main():
@@ -270,6 +314,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     roof, gemm_ms = gemm_roofline(dev, trk.n * 197, trk.dim, peaks) if rank == 0 else (None, 0.0)
+    hbm = hbm_kernels(dev, trk, frames_dev[1], peaks) if rank == 0 else None
     barrier()
 
     if rank == 0:
@@ -277,7 +322,7 @@ def main():
         value = n_total * args.steps / (ms_dev / 1e3)
         e2e_v = n_total * args.steps / (ms_e2e / 1e3)
         fl = flops_per_crop(MODEL)
-        roof["share_of_step"] = gemm_ms * 12 / ms_step
+        roof["share_of_step"] = gemm_ms * 12 / ms_step     # upper bound: the last block is CLS-only
         launches_per_step = trk.encoder.launches + 8      # + propagate, crop, loglik(2), sumexp,
         line = {                                          #   weights, resample, stats memset
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
@@ -291,7 +336,7 @@ def main():
                     "h2d_bytes_per_step": int(frames_host[0].numel()),
                     "d2h_bytes_per_step": 40},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roof, "clocks": clocks,
+            "roofline": roof, "hbm_kernels": hbm, "clocks": clocks,
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
             n_sample = 32

@@ -107,6 +107,26 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2v(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
+  unsigned long long rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fadd2v(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -228,53 +248,75 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tcgen05_fence_after();
       float inv_l = 0.f;
       if (warp_has_rows) {
-        uint32_t v[32];
-        // pass 1: row maximum over the 197 real keys
-        float m = -INFINITY;
-#pragma unroll 1
-        for (int ch = 0; ch < 6; ++ch) {
-          tmem_ld_32x32(tbuf + (uint32_t)(ch * 32), v);
-          tmem_ld_wait();
+        // Both passes are software-pipelined: the tcgen05.ld of chunk c+1 is in flight while
+        // chunk c is processed (two register buffers).  Chunks: 6 x 32 columns + 1 x 16.
+        uint32_t va[32], vb[32];
+        // ---- pass 1: row maximum over the 197 real keys (3-input max) ----
+        float m0 = -INFINITY, m1 = -INFINITY;
+        auto max_chunk = [&](const uint32_t (&v)[32]) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-        }
-        tmem_ld_32x16(tbuf + 192u, v);
+          for (int j = 0; j < 32; j += 4) {
+            m0 = max3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            m1 = max3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          }
+        };
+        tmem_ld_32x32(tbuf, va);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < kT - 192; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-        const float mc = m * c;
-        // pass 2: p = 2^(s c - m c), row sum, P (bf16 pairs) written in place over S
-        float l = 0.f;
-#pragma unroll 1
-        for (int ch = 0; ch < 6; ++ch) {
-          tmem_ld_32x32(tbuf + (uint32_t)(ch * 32), v);
+        for (int ch = 0; ch < 6; ch += 2) {
+          tmem_ld_32x32(tbuf + (uint32_t)((ch + 1) * 32), vb);
+          max_chunk(va);
           tmem_ld_wait();
+          if (ch + 2 < 6) tmem_ld_32x32(tbuf + (uint32_t)((ch + 2) * 32), va);
+          else tmem_ld_32x16(tbuf + 192u, va);
+          max_chunk(vb);
+          tmem_ld_wait();
+        }
+        m0 = max3(m0, __uint_as_float(va[0]), __uint_as_float(va[1]));
+        m1 = max3(m1, __uint_as_float(va[2]), __uint_as_float(va[3]));
+        const float m = max3(m0, m1, __uint_as_float(va[4]));        // keys 192..196
+        const float2 c2 = make_float2(c, c);
+        const float2 nmc2 = make_float2(-m * c, -m * c);
+        // ---- pass 2: p = 2^(s c - m c), row sum, P (bf16 pairs) written in place over S ----
+        float2 l2 = make_float2(0.f, 0.f);
+        auto exp_chunk = [&](const uint32_t (&v)[32], int ch) {
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float p0 = ex2(fmaf(__uint_as_float(v[2 * j]), c, -mc));
-            const float p1 = ex2(fmaf(__uint_as_float(v[2 * j + 1]), c, -mc));
-            l += p0 + p1;
-            pk[j] = pack2(p0, p1);
+            const float2 a = ffma2v(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])),
+                                    c2, nmc2);
+            const float2 p = make_float2(ex2(a.x), ex2(a.y));
+            l2 = fadd2v(l2, p);
+            pk[j] = pack2(p.x, p.y);
           }
           tmem_st_32x16(tbuf + (uint32_t)(ch * 16), pk);
+        };
+        tmem_ld_32x32(tbuf, va);
+        tmem_ld_wait();
+#pragma unroll
+        for (int ch = 0; ch < 6; ch += 2) {
+          tmem_ld_32x32(tbuf + (uint32_t)((ch + 1) * 32), vb);
+          exp_chunk(va, ch);
+          tmem_ld_wait();
+          if (ch + 2 < 6) tmem_ld_32x32(tbuf + (uint32_t)((ch + 2) * 32), va);
+          else tmem_ld_32x16(tbuf + 192u, va);
+          exp_chunk(vb, ch + 1);
+          tmem_ld_wait();
         }
         {
-          tmem_ld_32x16(tbuf + 192u, v);
-          tmem_ld_wait();
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int k0 = 192 + 2 * j;
-            const float p0 = (k0 < kT) ? ex2(fmaf(__uint_as_float(v[2 * j]), c, -mc)) : 0.f;
-            const float p1 = (k0 + 1 < kT) ? ex2(fmaf(__uint_as_float(v[2 * j + 1]), c, -mc)) : 0.f;
-            l += p0 + p1;
+            const float p0 = (k0 < kT) ? ex2(fmaf(__uint_as_float(va[2 * j]), c, nmc2.x)) : 0.f;
+            const float p1 = (k0 + 1 < kT) ? ex2(fmaf(__uint_as_float(va[2 * j + 1]), c, nmc2.x)) : 0.f;
+            l2.x += p0; l2.y += p1;
             pk[j] = pack2(p0, p1);
           }
           tmem_st_32x8(tbuf + 96u, pk);
         }
         tmem_st_wait();
-        inv_l = 1.0f / l;
+        inv_l = 1.0f / (l2.x + l2.y);
       }
       tcgen05_fence_before();
       __syncwarp();
