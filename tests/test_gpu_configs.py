@@ -1,0 +1,96 @@
+"""GPU: the remaining BASELINE configs at reduced / full scale.
+config 2/3 shape (ViT-B at full N): size-independent properties; config 4 model (ViT-L): parity;
+config 5 (independent needle streams): MultiStreamTracker == S single-stream Trackers."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pf
+from oracle.crop import crop_resize, patchify, boxes_from_state
+from oracle.vit import init_vit_weights, vit_forward, VIT_CONFIGS
+from gpu_util import cuda
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vit_large_matches_oracle():
+    from vitparticlefiltertracker_b200 import ops, pack_for_device
+    dev = cuda()
+    model, n = "vit_large_patch16_224", 2
+    cfg = VIT_CONFIGS[model]
+    sd = init_vit_weights(model)
+    rng = np.random.default_rng(3)
+    frame = rng.integers(0, 256, size=(240, 320, 3), dtype=np.uint8)
+    boxes = np.array([[160, 120, 64, 64], [100, 80, 90, 40]], dtype=np.float32)
+    crops = crop_resize(frame, boxes)
+    want = torch.from_numpy(vit_forward(crops, sd, model))
+    enc = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], n, pack_for_device(model, sd), dev)
+    got = enc.forward(torch.from_numpy(patchify(crops)).to(torch.bfloat16).to(dev), n).cpu()
+    rel = float((got - want).norm() / want.norm())
+    cos = torch.nn.functional.cosine_similarity(got, want, dim=1).min()
+    print(f"vit_large: rel-L2 {rel:.3e}, min cos {cos:.6f}")
+    assert rel < 1.5e-2 and cos > 1 - 1e-3
+
+
+def test_full_size_step_properties_vit_base_4096():
+    """BASELINE configs[2] at full size: properties that do not need the (317 s/frame) oracle."""
+    from vitparticlefiltertracker_b200 import Tracker
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+    dev = cuda()
+    frames, gt = make_clip("box", 1080, 1920, 3, seed=0, target=(96, 96))
+    n = 4096
+    trk = Tracker("vit_base_patch16_224", n, seed=0)
+    trk.init(frames[0], gt[0])
+    s1 = trk.step(frames[1])
+    assert s1.frame_idx == 1 and 1.0 <= s1.ess <= n and np.isfinite(s1.bbox).all()
+    w = trk.weights.cpu().numpy()
+    assert abs(float(w.astype(np.float64).sum()) - 1.0) < 1e-4 and (w >= 0).all()
+    idx = trk.idx.cpu().numpy()
+    assert (np.diff(idx) >= 0).all() and idx.min() >= 0 and idx.max() < n       # sortedness
+    assert np.array_equal(idx, pf.systematic_resample(w, trk.last_u))           # bit-exact K4
+    assert torch.equal(trk.particles, trk.propagated[:, trk.idx.long()])        # gather
+    counts = np.bincount(idx, minlength=n)
+    q = pf.snap_weights(w)
+    assert (np.abs(counts - n * q / q.sum()) < 1 + 1e-6).all()
+    # crop parity on a sample of the real particle boxes (K1 at the 1080p frame size)
+    st = trk.propagated.cpu().numpy()
+    sel = np.arange(0, n, 512)
+    want = patchify(crop_resize(frames[1], boxes_from_state(st[:, sel], trk.w0, trk.h0)))
+    got = trk.patches.view(n, 196, 768)[torch.from_numpy(sel).to(dev)].reshape(-1, 768).float().cpu().numpy()
+    want_bf = torch.from_numpy(want).to(torch.bfloat16).float().numpy()
+    assert np.abs(got - want_bf).max() <= 2.0 ** -7
+    # batch invariance at full size: the first 8 crops alone give bit-identical embeddings
+    emb_full = trk.emb[:8].clone()
+    small = trk.encoder.forward(trk.patches[:8 * 196].contiguous(), 8)
+    assert torch.equal(small, emb_full)
+    # embedding parity against the oracle on those 8 crops
+    want_emb = vit_forward(crop_resize(frames[1], boxes_from_state(st[:, :8], trk.w0, trk.h0)),
+                           init_vit_weights("vit_base_patch16_224"), "vit_base_patch16_224")
+    cos = torch.nn.functional.cosine_similarity(emb_full.cpu(), torch.from_numpy(want_emb), dim=1)
+    assert cos.min() > 1 - 1e-3
+    s2 = trk.step(frames[2])
+    assert s2.frame_idx == 2 and np.isfinite(s2.bbox).all()
+
+
+def test_multistream_equals_independent_trackers():
+    from vitparticlefiltertracker_b200 import Tracker, MultiStreamTracker
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+    cuda()
+    S, n = 3, 128
+    clips = [make_clip("needle", 240, 320, 4, seed=s, target=(3, 120)) for s in range(S)]
+    frames = np.stack([c[0] for c in clips], axis=1)            # [F, S, H, W, 3]
+    boxes = [c[1][0] for c in clips]
+    ms = MultiStreamTracker(S, "vit_tiny_patch16_224", n, seed=4)
+    ms.init(frames[0], boxes)
+    singles = []
+    for s in range(S):
+        t = Tracker("vit_tiny_patch16_224", n, seed=4, stream_id=s)
+        t.init(frames[0, s], boxes[s])
+        singles.append(t)
+    for f in range(1, 4):
+        states = ms.step(frames[f])
+        for s in range(S):
+            ref = singles[s].step(frames[f, s])
+            assert torch.equal(ms.particles[s], singles[s].particles)      # bit-identical filter
+            assert torch.equal(ms.idx[s], singles[s].idx)
+            assert np.allclose(states[s].bbox, ref.bbox, atol=1e-9) and states[s].frame_idx == f

@@ -2,12 +2,17 @@
 // Oracle: oracle/crop.py crop_resize + patchify (upstream anchor
 // README.md:7, the input side of ViT feature extraction).
 //
-// HBM-write bound: 3*224*224 bf16 = 301 056 B written per particle; the uint8 frame (<= 6.2 MB)
-// is read through L1/L2.  One CTA handles PATCHES_PER_CTA patches of one crop; one warp writes
-// one 16x16 patch per iteration as three 512-byte contiguous runs (one per channel), each lane
-// producing 8 consecutive pixels (one 16-byte store per channel).  The arithmetic mirrors the
-// oracle's fp32 operation order with explicit round-to-nearest intrinsics (no FMA contraction),
-// so the result equals bf16(oracle) bit for bit.
+// HBM-write bound by construction: 3*224*224 bf16 = 301 056 B written per particle; the uint8
+// frame (<= 6.2 MB) lives in L2.  One CTA produces two patch rows (32 x 224 output pixels) of
+// one crop:
+//   1. the particle box and the 224 horizontal taps (x0, frac) -- identical for every output
+//      row of the crop -- are staged in shared memory once per CTA;
+//   2. the source rows the CTA touches are copied to shared memory with coalesced 4-byte loads
+//      (falls back to direct global taps when the box is too large to stage);
+//   3. one warp writes one 16x16 patch per iteration as three 512-byte contiguous runs (one per
+//      channel), each lane producing 8 consecutive pixels (one 16-byte store per channel).
+// The arithmetic mirrors the oracle's fp32 operation order with explicit round-to-nearest
+// intrinsics (no FMA contraction), so the result equals bf16(oracle) bit for bit.
 #include "common.cuh"
 
 namespace vpf {
@@ -17,8 +22,10 @@ static constexpr int kPatch = 16;
 static constexpr int kGridP = 14;
 static constexpr int kPatches = 196;
 static constexpr int kPatchK = 768;
-static constexpr int kSplit = 7;                       // CTAs per crop
+static constexpr int kSplit = 7;                          // CTAs per crop
 static constexpr int kPatchesPerCta = kPatches / kSplit;  // 28 = two patch rows
+static constexpr int kRowsPerCta = 2 * kPatch;            // 32 output rows
+static constexpr int kStageWords = 9 * 1024;              // 36 KB of staged source rows
 
 struct Box {
   float cx, cy, w, h;
@@ -34,6 +41,9 @@ __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ f
                                                     const float* __restrict__ src, int n, int ld,
                                                     float w0, float h0,
                                                     __nv_bfloat16* __restrict__ out) {
+  __shared__ uint32_t stage[kStageWords];
+  __shared__ float s_fx[kCrop];
+  __shared__ int s_x0[kCrop];
   const int crop = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Box b;
@@ -51,8 +61,44 @@ __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ f
   const float basex = __fsub_rn(__fsub_rn(b.cx, __fmul_rn(0.5f, b.w)), 0.5f);
   const float basey = __fsub_rn(__fsub_rn(b.cy, __fmul_rn(0.5f, b.h)), 0.5f);
   const float xmax = (float)(W - 1), ymax = (float)(H - 1);
-  const int ky = lane >> 1, kx0 = (lane & 1) * 8;
   const float c255 = 2.0f / 255.0f;
+  const int i0 = blockIdx.y * kRowsPerCta;
+
+  // ---- horizontal taps, shared by every output row ----
+  if (threadIdx.x < kCrop) {
+    const float xs = sample_coord(basex, stepx, threadIdx.x, xmax);
+    const float x0f = floorf(xs);
+    s_fx[threadIdx.x] = __fsub_rn(xs, x0f);
+    s_x0[threadIdx.x] = (int)x0f;
+  }
+  // ---- source window of this CTA (coordinates are monotone in the output index) ----
+  const int y_lo = (int)floorf(sample_coord(basey, stepy, i0, ymax));
+  const int y_hi = min((int)floorf(sample_coord(basey, stepy, i0 + kRowsPerCta - 1, ymax)) + 1, H - 1);
+  const int x_lo = (int)floorf(sample_coord(basex, stepx, 0, xmax));
+  const int x_hi = min((int)floorf(sample_coord(basex, stepx, kCrop - 1, xmax)) + 1, W - 1);
+  const int rows = y_hi - y_lo + 1;
+  const int row_bytes = (x_hi - x_lo + 1) * 3;
+  const int pitch = (row_bytes + 6) / 4 + 1;                  // words per staged row
+  const bool staged = rows * pitch <= kStageWords;
+  if (staged) {
+    const uintptr_t end = reinterpret_cast<uintptr_t>(frame) + (size_t)H * W * 3;
+    for (int idx = threadIdx.x; idx < rows * pitch; idx += 256) {
+      const int r = idx / pitch, wd = idx - r * pitch;
+      const uintptr_t g0 = reinterpret_cast<uintptr_t>(frame) + ((size_t)(y_lo + r) * W + x_lo) * 3;
+      const uintptr_t ga = (g0 & ~(uintptr_t)3) + (uintptr_t)wd * 4;   // 4-byte aligned word
+      uint32_t v = 0;
+      if (ga + 4 <= end) {
+        v = __ldg(reinterpret_cast<const uint32_t*>(ga));
+      } else {
+        for (int k = 0; k < 4; ++k)
+          if (ga + k < end) v |= (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(ga + k)) << (8 * k);
+      }
+      stage[idx] = v;
+    }
+  }
+  __syncthreads();
+  const uint8_t* sbytes = reinterpret_cast<const uint8_t*>(stage);
+  const int ky = lane >> 1, kx0 = (lane & 1) * 8;
 
   for (int pl = warp; pl < kPatchesPerCta; pl += 8) {
     const int p = blockIdx.y * kPatchesPerCta + pl;
@@ -61,22 +107,31 @@ __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ f
     const float ys = sample_coord(basey, stepy, i, ymax);
     const float y0f = floorf(ys);
     const float fy = __fsub_rn(ys, y0f);
+    const float gy = __fsub_rn(1.0f, fy);
     const int y0 = (int)y0f, y1 = min(y0 + 1, H - 1);
-    const uint8_t* row0 = frame + (size_t)y0 * W * 3;
-    const uint8_t* row1 = frame + (size_t)y1 * W * 3;
+    const uint8_t* tap = staged ? sbytes : frame;
+    long long off0, off1;
+    if (staged) {
+      // a staged row starts at the 4-byte aligned address at or below its first pixel (x_lo)
+      const int sh0 = (int)((reinterpret_cast<uintptr_t>(frame) + ((size_t)y0 * W + x_lo) * 3) & 3);
+      const int sh1 = (int)((reinterpret_cast<uintptr_t>(frame) + ((size_t)y1 * W + x_lo) * 3) & 3);
+      off0 = (long long)(y0 - y_lo) * pitch * 4 + sh0 - x_lo * 3;
+      off1 = (long long)(y1 - y_lo) * pitch * 4 + sh1 - x_lo * 3;
+    } else {
+      off0 = (long long)y0 * W * 3;
+      off1 = (long long)y1 * W * 3;
+    }
     __align__(16) __nv_bfloat16 v[3][8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int j = px * kPatch + kx0 + e;
-      const float xs = sample_coord(basex, stepx, j, xmax);
-      const float x0f = floorf(xs);
-      const float fx = __fsub_rn(xs, x0f);
-      const int x0 = (int)x0f, x1 = min(x0 + 1, W - 1);
-      const float gx = __fsub_rn(1.0f, fx), gy = __fsub_rn(1.0f, fy);
+      const float fx = s_fx[j];
+      const int x0 = s_x0[j], x1 = min(x0 + 1, W - 1);
+      const float gx = __fsub_rn(1.0f, fx);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float p00 = (float)__ldg(row0 + x0 * 3 + c), p01 = (float)__ldg(row0 + x1 * 3 + c);
-        float p10 = (float)__ldg(row1 + x0 * 3 + c), p11 = (float)__ldg(row1 + x1 * 3 + c);
+        float p00 = (float)tap[off0 + x0 * 3 + c], p01 = (float)tap[off0 + x1 * 3 + c];
+        float p10 = (float)tap[off1 + x0 * 3 + c], p11 = (float)tap[off1 + x1 * 3 + c];
         float top = __fadd_rn(__fmul_rn(gx, p00), __fmul_rn(fx, p01));
         float bot = __fadd_rn(__fmul_rn(gx, p10), __fmul_rn(fx, p11));
         float val = __fadd_rn(__fmul_rn(gy, top), __fmul_rn(fy, bot));
