@@ -274,6 +274,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     pg = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     n_gpus = world
