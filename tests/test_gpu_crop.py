@@ -44,3 +44,21 @@ def test_crop_state_matches_oracle():
     got = ops.crop_state(torch.from_numpy(frame).to(dev), torch.from_numpy(st).to(dev), 48.0, 32.0)
     diff = np.abs(got.float().cpu().numpy() - want)
     assert diff.max() <= 2.0 ** -7
+
+
+@pytest.mark.parametrize("H,W", [(243, 321), (97, 131)])
+def test_crop_odd_frame_sizes_and_unaligned_views(H, W):
+    """Row pitches that are not multiples of 4 bytes and frames that start at an odd byte offset
+    (a slice of a clip tensor) exercise the staged-row alignment logic."""
+    from vitparticlefiltertracker_b200 import ops
+    dev = cuda()
+    rng = np.random.default_rng(W)
+    clip = rng.integers(0, 256, size=(3, H, W, 3), dtype=np.uint8)
+    clip_dev = torch.from_numpy(clip).to(dev)
+    boxes = np.array([[W / 2, H / 2, 40, 30], [3, 3, 20, 20], [W - 2, H - 2, 30, 30],
+                      [W / 2 + 0.3, H / 2 - 0.7, W * 1.5, H * 1.5], [W / 3, H / 3, 8.5, 120.25]],
+                     dtype=np.float32)
+    for f in range(3):                                   # frame f starts at byte f*H*W*3
+        want = _bf16(patchify(crop_resize(clip[f], boxes)))
+        got = ops.crop_boxes(clip_dev[f], torch.from_numpy(boxes).to(dev)).float().cpu().numpy()
+        assert np.abs(got - want).max() <= 2.0 ** -7

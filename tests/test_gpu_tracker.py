@@ -54,3 +54,24 @@ def test_step_before_init_raises_and_bad_frame():
         trk.step(np.zeros((32, 32, 3), np.uint8))
     with pytest.raises(ValueError):
         trk.init(np.zeros((32, 32), np.uint8), (0, 0, 8, 8))
+
+
+def test_odd_particle_count_and_partly_outside_bbox():
+    """n_particles that is not a multiple of any tile size, a bbox hanging over the frame edge."""
+    from vitparticlefiltertracker_b200 import Tracker
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+    cuda()
+    frames, _ = make_clip("box", 120, 160, 3, seed=3, target=(32, 24))
+    n = 100
+    bbox = (140.0, 100.0, 40.0, 30.0)                      # extends beyond the 160x120 frame
+    ora = OracleTracker("vit_tiny_patch16_224", n, seed=9)
+    trk = Tracker("vit_tiny_patch16_224", n, seed=9)
+    ora.init(frames[0], bbox)
+    trk.init(frames[0], bbox)
+    trk.particles.copy_(torch.from_numpy(ora.particles))
+    so, sg = ora.step(frames[1]), trk.step(frames[1])
+    assert np.abs(trk.propagated.cpu().numpy() - ora.last["propagated"]).max() < 2e-5
+    assert np.abs(trk.logw.cpu().numpy() * np.float32(0.1) - ora.last["cos"]).max() < 5e-3
+    assert np.abs(np.array(sg.bbox) - np.array(so.bbox)).max() < 0.5
+    assert np.array_equal(trk.idx.cpu().numpy(),
+                          pf.systematic_resample(trk.weights.cpu().numpy(), trk.last_u))
