@@ -129,7 +129,8 @@ def run_reference(args):
     if rank != 0:
         return
     from vitparticlefiltertracker_b200.synthetic import make_clip
-    frames, gt = make_clip("box", FRAME_HW[0], FRAME_HW[1], 6, seed=0, target=TARGET)
+    frames, gt = make_clip("box", FRAME_HW[0], FRAME_HW[1], 6, seed=0, target=TARGET,
+                           velocity=(3.0, 1.0))
     n_sample = 32
     steps = max(1, min(args.steps, 4))
     warmup = max(0, min(args.warmup, 1))
@@ -214,6 +215,42 @@ def gemm_roofline(dev, M, D, peaks, reps=2):
             "flops_per_launch_set": tot_fl, "ms_per_launch_set": tot_ms, "detail": detail}, tot_ms
 
 
+def stage_times(dev, trk, frame, iters=5):
+    """Per-stage device times of one step (CUDA events), SURVEY.md section 8d: K1 crop, K2 ViT
+    encoder, K3 particle update (motion + likelihood + normalisation), K4 resampling."""
+    from vitparticlefiltertracker_b200 import ops
+
+    def t(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / iters
+
+    n, xch = trk.n, trk.xch
+    total, cdf, _ = xch.local_views()
+    st = trk.particles.clone()
+    nxt = torch.empty_like(st)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    stats = torch.zeros(5, dtype=torch.float64, device=dev)
+
+    def k3():
+        ops.propagate(st, 0.0, 0.0, 0.0, 0, 1)
+        ops.loglik(trk.emb, trk.template, trk.tau, trk.logw, xch.max_local)
+        ops.sumexp(trk.logw, xch.max_all, xch.sum_local)
+        ops.weights(trk.logw, xch.max_all, xch.sum_all, st, trk.weights, cdf, total, stats)
+
+    return {"K1_crop_ms": t(lambda: ops.crop_state(frame, st, trk.w0, trk.h0, trk.patches)),
+            "K2_vit_ms": t(lambda: trk.encoder.forward(trk.patches, n, trk.emb)),
+            "K3_particle_update_ms": t(k3),
+            "K4_resample_ms": t(lambda: ops.resample(cdf.view(1, -1), total, n, 0, 0.37, st, nxt, idx))}
+
+
 def hbm_kernels(dev, trk, frame, peaks, iters=10):
     """K1 (crop) and K3/K4 (particle update + resampling) timed alone with CUDA events: achieved
     HBM GB/s on their algorithmic bytes against the measured copy peak."""
@@ -263,7 +300,7 @@ def main():
 
     import torch.distributed as dist
     from vitparticlefiltertracker_b200 import Tracker, flops_per_crop
-    from vitparticlefiltertracker_b200.synthetic import make_clip
+    from vitparticlefiltertracker_b200.synthetic import iou, make_clip
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -282,7 +319,8 @@ def main():
     n_total = PARTICLES_PER_GPU * n_gpus
     peaks = load_peaks()
 
-    frames, gt = make_clip("box", FRAME_HW[0], FRAME_HW[1], CLIP_FRAMES, seed=0, target=TARGET)
+    frames, gt = make_clip("box", FRAME_HW[0], FRAME_HW[1], CLIP_FRAMES, seed=0, target=TARGET,
+                           velocity=(3.0, 1.0))
     frames_host = torch.from_numpy(frames).pin_memory()
     frames_dev = torch.from_numpy(frames).to(dev)
     trk = Tracker(MODEL, n_total, seed=0, device=dev, process_group=pg)
@@ -293,14 +331,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    ious = []
+
     def timed(frames_src, steps, warmup):
         for i in range(warmup):
-            trk.step(frames_src[1 + i % (CLIP_FRAMES - 1)])
+            f = 1 + i % (CLIP_FRAMES - 1)
+            ious.append(iou(trk.step(frames_src[f]).bbox, gt[f]))
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for i in range(steps):
-            trk.step(frames_src[1 + (warmup + i) % (CLIP_FRAMES - 1)])
+            f = 1 + (warmup + i) % (CLIP_FRAMES - 1)
+            ious.append(iou(trk.step(frames_src[f]).bbox, gt[f]))
         e.record()
         barrier()
         ms = torch.tensor([s.elapsed_time(e)], device=dev)
@@ -317,16 +359,21 @@ def main():
 
     roof, gemm_ms = gemm_roofline(dev, trk.n * 197, trk.dim, peaks) if rank == 0 else (None, 0.0)
     hbm = hbm_kernels(dev, trk, frames_dev[1], peaks) if rank == 0 else None
+    stages = stage_times(dev, trk, frames_dev[1]) if rank == 0 else None
     barrier()
 
+    tracking = {"mean_iou_vs_ground_truth": float(np.mean(ious[: args.warmup + args.steps])),
+                "frames": args.warmup + args.steps,
+                "note": "seeded random-init ViT features (no pretrained weights offline); "
+                        "consecutive clip frames, free-running filter"}
     if rank == 0:
         ms_step = ms_dev / args.steps
         value = n_total * args.steps / (ms_dev / 1e3)
         e2e_v = n_total * args.steps / (ms_e2e / 1e3)
         fl = flops_per_crop(MODEL)
         roof["share_of_step"] = gemm_ms * 12 / ms_step     # upper bound: the last block is CLS-only
-        launches_per_step = trk.encoder.launches + 8      # + propagate, crop, loglik(2), sumexp,
-        line = {                                          #   weights, resample, stats memset
+        launches_per_step = trk.encoder.launches + 7      # + propagate, crop, loglik, max_reduce,
+        line = {                                          #   sumexp, weights, resample
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -338,7 +385,8 @@ def main():
                     "h2d_bytes_per_step": int(frames_host[0].numel()),
                     "d2h_bytes_per_step": 40},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roof, "hbm_kernels": hbm, "clocks": clocks,
+            "roofline": roof, "hbm_kernels": hbm, "stages_ms": stages, "tracking": tracking,
+            "clocks": clocks,
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
             n_sample = 32

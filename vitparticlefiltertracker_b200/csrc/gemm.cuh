@@ -52,7 +52,7 @@ struct EpiCfg {
   static_assert(kColsPerWarp % 32 == 0, "epilogue column split must be a multiple of 32");
 };
 
-template <int BLOCK_N, int CTAS>
+template <int BLOCK_N, int CTAS, int MODE>
 struct GemmCfg {
   // CTAS = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x BLOCK_N tile; each CTA
   // stages its own 128 rows of A and HALF of the W tile, so shared-memory fill traffic from L2
@@ -62,7 +62,7 @@ struct GemmCfg {
   static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSlabBytes = 4096;  // per epilogue warp: 32 rows x 128 B transpose slab
-  static constexpr int kEpiBytes = 8 * kSlabBytes;      // 8 x 4 KB (fp32) or 16 x 2 KB (bf16)
+  static constexpr int kEpiBytes = EpiCfg<BLOCK_N, MODE>::kWarps * ((MODE <= 1) ? 2048 : 4096);
   static constexpr int kStagesMax = (227 * 1024 - kEpiBytes - 1024 - 256) / kStageBytes;
   static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
   static constexpr int kTmemCols = (2 * BLOCK_N > 256) ? 512 : 256;
@@ -209,7 +209,7 @@ template <int BLOCK_N, int MODE, int CTAS>
 __global__ void __launch_bounds__((EpiCfg<BLOCK_N, MODE>::kThreads), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmArgs g) {
-  using Cfg = GemmCfg<BLOCK_N, CTAS>;
+  using Cfg = GemmCfg<BLOCK_N, CTAS, MODE>;
   using Epi = EpiCfg<BLOCK_N, MODE>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];

@@ -116,7 +116,7 @@ static int gemm_ctas() {
 template <int BLOCK_N, int MODE, int CTAS>
 static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g,
                          cudaStream_t s) {
-  using Cfg = GemmCfg<BLOCK_N, CTAS>;
+  using Cfg = GemmCfg<BLOCK_N, CTAS, MODE>;
   auto kern = gemm_bf16_kernel<BLOCK_N, MODE, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {

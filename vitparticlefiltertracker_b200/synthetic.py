@@ -31,12 +31,14 @@ def _value_noise(rng, H, W, cell=8):
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
-def make_clip(kind="box", H=224, W=224, n_frames=32, seed=0, target=(48, 48)):
+def make_clip(kind="box", H=224, W=224, n_frames=32, seed=0, target=(48, 48), velocity=None):
     """Returns (frames uint8 [F,H,W,3], gt float32 [F,4] as (x, y, w, h) top-left boxes).
 
     kind="box":    random-texture rectangle, centre c(t) = c0 + v t + A sin(2 pi t / P).
     kind="needle": thin bright bar (3 px x 120 px) rotating 1 degree per frame about a moving
                    centre; gt is the axis-aligned bounding box of the bar.
+    velocity: optional (vx, vy) px/frame of the linear part (default: cross 30 % of the width
+              and 10 % of the height over the clip).
     """
     rng = np.random.Generator(np.random.Philox(key=int(seed)))
     bg = _value_noise(rng, H, W)
@@ -47,6 +49,8 @@ def make_clip(kind="box", H=224, W=224, n_frames=32, seed=0, target=(48, 48)):
     margin = max(tw, th)
     span = np.array([W * 0.3, H * 0.1])
     vel = span / max(n_frames - 1, 1)
+    if velocity is not None:                      # explicit (vx, vy) in pixels per frame
+        vel = np.array(velocity, dtype=np.float64)
     amp = np.array([0.0, min(H * 0.08, margin * 0.5)])
     period = 24.0
     if kind == "box":

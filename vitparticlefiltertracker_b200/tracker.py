@@ -116,9 +116,9 @@ class Tracker:
         self.weights.fill_(1.0 / self.n_global)
         self.frame_idx = 0
 
-    def step(self, frame, _noise=None, _u=None, _emb=None) -> State:
-        """One tracked frame.  `_noise` ([6,n] normals), `_u` (resampling uniform) and `_emb`
-        ([n,D] embeddings) are test hooks that inject oracle quantities (teacher forcing)."""
+    def step(self, frame, _u=None, _emb=None) -> State:
+        """One tracked frame.  `_u` (resampling uniform) and `_emb` ([n,D] device embeddings) are
+        test hooks that inject oracle quantities; every computation still runs in libvpf."""
         if self.frame_idx < 0:
             raise RuntimeError("call init(frame, bbox) before step(frame)")
         frame = self._to_device_frame(frame)
@@ -126,11 +126,8 @@ class Tracker:
         t = self.frame_idx
         st = self.particles
         # a3 motion
-        if _noise is None:
-            ops.propagate(st, self.sigma_pos, self.sigma_vel, self.sigma_scale, self.seed, t,
-                          self.stream_id, self.id_offset)
-        else:
-            self._propagate_with(_noise)
+        ops.propagate(st, self.sigma_pos, self.sigma_vel, self.sigma_scale, self.seed, t,
+                      self.stream_id, self.id_offset)
         # a4 crop, a5 ViT
         if _emb is None:
             ops.crop_state(frame, st, self.w0, self.h0, self.patches)
@@ -167,18 +164,3 @@ class Tracker:
         w = self.w0 * math.exp(sc)
         h = self.h0 * math.exp(sc)
         return State((cx - 0.5 * w, cy - 0.5 * h, w, h), ess, t)
-
-    def _propagate_with(self, noise):
-        """Test hook: the motion update with externally supplied normals (torch elementwise on
-        the device; not part of the product path)."""
-        z = noise.to(self.device, torch.float32)
-        st = self.particles
-        sp, sv, ss = [torch.tensor(v, dtype=torch.float32, device=self.device)
-                      for v in (self.sigma_pos, self.sigma_vel, self.sigma_scale)]
-        new = st.clone()
-        new[0] = (st[0] + st[2]) + sp * z[0]
-        new[1] = (st[1] + st[3]) + sp * z[1]
-        new[2] = st[2] + sv * z[2]
-        new[3] = st[3] + sv * z[3]
-        new[4] = st[4] + ss * z[4]
-        st.copy_(new)
