@@ -62,6 +62,13 @@ int vpf_init_particles(float* state, int n, int ld, float cx, float cy, float si
 int vpf_propagate(float* state, int n, int ld, float sigma_pos, float sigma_vel,
                   float sigma_scale, uint64_t seed, uint32_t frame_idx, uint32_t stream_id,
                   uint32_t id_offset, void* stream);
+/* CUDA-graph variants: the frame counter lives in device memory (advanced by vpf_frame_advance),
+ * so one captured graph can be replayed for every frame.  Same arithmetic as the host-argument
+ * forms; vpf_resample_dev derives the frame's uniform from (seed, *frame_idx_dev, stream_id).  */
+int vpf_frame_advance(uint32_t* frame_idx_dev, void* stream);
+int vpf_propagate_dev(float* state, int n, int ld, float sigma_pos, float sigma_vel,
+                      float sigma_scale, uint64_t seed, const uint32_t* frame_idx_dev,
+                      uint32_t stream_id, uint32_t id_offset, void* stream);
 /* test hooks: raw Philox words [4][n] for counters (id_offset+i, c1, c2, c3); the six normals
  * [6][n] that propagate consumes; the fp64 resampling uniform (host, no device work).        */
 int vpf_philox_fill(uint32_t* out, int n, uint32_t id_offset, uint32_t c1, uint32_t c2,
@@ -130,6 +137,11 @@ int vpf_weights(const float* logw, int n, const float* rank_max, const double* r
 int vpf_resample(const double* cdf_all, const double* totals, int R, int n_local,
                  uint32_t id_offset, double u, const float* state_all, float* state_out,
                  int ld_out, int32_t* idx, void* stream);
+
+int vpf_resample_dev(const double* cdf_all, const double* totals, int R, int n_local,
+                     uint32_t id_offset, uint64_t seed, uint32_t stream_id,
+                     const uint32_t* frame_idx_dev, const float* state_all, float* state_out,
+                     int ld_out, int32_t* idx, void* stream);
 
 #ifdef __cplusplus
 }

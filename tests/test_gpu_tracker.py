@@ -75,3 +75,23 @@ def test_odd_particle_count_and_partly_outside_bbox():
     assert np.abs(np.array(sg.bbox) - np.array(so.bbox)).max() < 0.5
     assert np.array_equal(trk.idx.cpu().numpy(),
                           pf.systematic_resample(trk.weights.cpu().numpy(), trk.last_u))
+
+
+def test_cuda_graph_mode_is_bit_identical_to_eager():
+    """Tracker(cuda_graph=True) replays one captured graph per frame (device-side frame counter and
+    resampling uniform); it must follow the eager tracker bit for bit."""
+    from vitparticlefiltertracker_b200 import Tracker
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+    cuda()
+    frames, gt = make_clip("box", 224, 224, 8, seed=1, target=(48, 48))
+    eager = Tracker("vit_tiny_patch16_224", 256, seed=5)
+    graph = Tracker("vit_tiny_patch16_224", 256, seed=5, cuda_graph=True)
+    eager.init(frames[0], gt[0])
+    graph.init(frames[0], gt[0])
+    for t in range(1, 8):
+        a, b = eager.step(frames[t]), graph.step(frames[t])
+        assert a.frame_idx == b.frame_idx == t and eager.last_u == graph.last_u
+        assert torch.equal(eager.particles, graph.particles), t
+        assert torch.equal(eager.idx, graph.idx) and torch.equal(eager.weights, graph.weights)
+        assert a.bbox == b.bbox and a.ess == b.ess
+    assert graph._graph is not None

@@ -24,6 +24,11 @@ SIGNATURES = {
                                     _u32, _u32, _c_void_p]),
     "vpf_propagate": (_c_int, [_c_void_p, _c_int, _c_int, _c_float, _c_float, _c_float, _u64, _u32,
                                _u32, _u32, _c_void_p]),
+    "vpf_frame_advance": (_c_int, [_c_void_p, _c_void_p]),
+    "vpf_propagate_dev": (_c_int, [_c_void_p, _c_int, _c_int, _c_float, _c_float, _c_float, _u64,
+                                   _c_void_p, _u32, _u32, _c_void_p]),
+    "vpf_resample_dev": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _u32, _u64, _u32, _c_void_p,
+                                  _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p]),
     "vpf_philox_fill": (_c_int, [_c_void_p, _c_int, _u32, _u32, _u32, _u32, _u64, _c_void_p]),
     "vpf_normals_fill": (_c_int, [_c_void_p, _c_int, _u32, _u32, _u32, _u64, _c_void_p]),
     "vpf_resample_uniform": (_c_double, [_u64, _u32, _u32]),

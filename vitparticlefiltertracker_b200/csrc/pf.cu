@@ -72,10 +72,12 @@ __global__ void init_particles_kernel(float* __restrict__ st, int n, int ld, flo
 
 // constant velocity, dt = 1: positions use the velocity from before this step's velocity noise
 __global__ void propagate_kernel(float* __restrict__ st, int n, int ld, float sp, float sv,
-                                 float ss, uint32_t frame_idx, uint32_t stream_id,
+                                 float ss, uint32_t frame_idx,
+                                 const uint32_t* __restrict__ frame_idx_dev, uint32_t stream_id,
                                  uint32_t id_offset, uint32_t k0, uint32_t k1) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (frame_idx_dev) frame_idx = *frame_idx_dev;   // CUDA-graph replay: the counter lives on device
   float z[6];
   six_normals(id_offset + (uint32_t)i, frame_idx, stream_id, k0, k1, z);
   float cx = st[0 * (size_t)ld + i], cy = st[1 * (size_t)ld + i];
@@ -235,9 +237,15 @@ __global__ void __launch_bounds__(1024) weights_kernel(
 // ---- systematic resampling + gather --------------------------------------------------------
 __global__ void __launch_bounds__(256) resample_kernel(
     const double* __restrict__ cdf_all, const double* __restrict__ totals, int R, int n_local,
-    uint32_t id_offset, double u, const float* __restrict__ state_all,
+    uint32_t id_offset, double u, const uint32_t* __restrict__ frame_idx_dev, uint32_t k0,
+    uint32_t k1, uint32_t stream_id, const float* __restrict__ state_all,
     float* __restrict__ state_out, int ld_out, int32_t* __restrict__ idx) {
   extern __shared__ double offs[];  // [R] exclusive prefix of rank totals
+  if (frame_idx_dev) {              // CUDA-graph replay: derive the frame's uniform on device
+    Philox4 r = philox4x32_10(0xFFFFFFFFu, *frame_idx_dev, stream_id, 2u, k0, k1);
+    const uint64_t v = (((uint64_t)r.v[0] << 21) ^ ((uint64_t)r.v[1] >> 11)) & ((1ull << 53) - 1);
+    u = (double)v * (1.0 / 9007199254740992.0);
+  }
   if (threadIdx.x == 0) {
     double a = 0.0;
     for (int r = 0; r < R; ++r) { offs[r] = a; a = __dadd_rn(a, totals[r]); }
@@ -319,7 +327,29 @@ int vpf_propagate(float* state, int n, int ld, float sigma_pos, float sigma_vel,
   VPF_REQUIRE(state && n > 0 && ld >= n, "vpf_propagate: bad arguments");
   uint32_t k0, k1; split_seed(seed, k0, k1);
   propagate_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      state, n, ld, sigma_pos, sigma_vel, sigma_scale, frame_idx, stream_id, id_offset, k0, k1);
+      state, n, ld, sigma_pos, sigma_vel, sigma_scale, frame_idx, nullptr, stream_id, id_offset, k0,
+      k1);
+  VPF_LAUNCH_CHECK();
+  return VPF_OK;
+}
+
+__global__ void frame_advance_kernel(uint32_t* f) { *f += 1u; }
+
+int vpf_frame_advance(uint32_t* frame_idx_dev, void* stream) {
+  VPF_REQUIRE(frame_idx_dev, "vpf_frame_advance: null argument");
+  frame_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(frame_idx_dev);
+  VPF_LAUNCH_CHECK();
+  return VPF_OK;
+}
+
+int vpf_propagate_dev(float* state, int n, int ld, float sigma_pos, float sigma_vel,
+                      float sigma_scale, uint64_t seed, const uint32_t* frame_idx_dev,
+                      uint32_t stream_id, uint32_t id_offset, void* stream) {
+  VPF_REQUIRE(state && frame_idx_dev && n > 0 && ld >= n, "vpf_propagate_dev: bad arguments");
+  uint32_t k0, k1; split_seed(seed, k0, k1);
+  propagate_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      state, n, ld, sigma_pos, sigma_vel, sigma_scale, 0u, frame_idx_dev, stream_id, id_offset, k0,
+      k1);
   VPF_LAUNCH_CHECK();
   return VPF_OK;
 }
@@ -364,7 +394,24 @@ int vpf_resample(const double* cdf_all, const double* totals, int R, int n_local
               "vpf_resample: bad arguments (need 0 <= u < 1)");
   VPF_REQUIRE((long long)R * n_local < (1ll << 31), "vpf_resample: too many particles");
   resample_kernel<<<(n_local + 255) / 256, 256, R * sizeof(double), (cudaStream_t)stream>>>(
-      cdf_all, totals, R, n_local, id_offset, u, state_all, state_out, ld_out, idx);
+      cdf_all, totals, R, n_local, id_offset, u, nullptr, 0u, 0u, 0u, state_all, state_out, ld_out,
+      idx);
+  VPF_LAUNCH_CHECK();
+  return VPF_OK;
+}
+
+int vpf_resample_dev(const double* cdf_all, const double* totals, int R, int n_local,
+                     uint32_t id_offset, uint64_t seed, uint32_t stream_id,
+                     const uint32_t* frame_idx_dev, const float* state_all, float* state_out,
+                     int ld_out, int32_t* idx, void* stream) {
+  VPF_REQUIRE(cdf_all && totals && state_all && state_out && idx && frame_idx_dev && R > 0 &&
+                  n_local > 0 && ld_out >= n_local,
+              "vpf_resample_dev: bad arguments");
+  VPF_REQUIRE((long long)R * n_local < (1ll << 31), "vpf_resample_dev: too many particles");
+  uint32_t k0, k1; split_seed(seed, k0, k1);
+  resample_kernel<<<(n_local + 255) / 256, 256, R * sizeof(double), (cudaStream_t)stream>>>(
+      cdf_all, totals, R, n_local, id_offset, 0.0, frame_idx_dev, k0, k1, stream_id, state_all,
+      state_out, ld_out, idx);
   VPF_LAUNCH_CHECK();
   return VPF_OK;
 }

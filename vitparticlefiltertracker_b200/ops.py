@@ -42,6 +42,28 @@ def propagate(state, sigma_pos, sigma_vel, sigma_scale, seed, frame_idx, stream_
                                          _stream()), "vpf_propagate")
 
 
+def frame_advance(frame_idx_dev):
+    _lib.check(_lib.load().vpf_frame_advance(frame_idx_dev.data_ptr(), _stream()), "vpf_frame_advance")
+
+
+def propagate_dev(state, sigma_pos, sigma_vel, sigma_scale, seed, frame_idx_dev, stream_id=0,
+                  id_offset=0):
+    _dev(state, torch.float32)
+    _lib.check(_lib.load().vpf_propagate_dev(state.data_ptr(), state.shape[1], state.stride(0),
+                                             sigma_pos, sigma_vel, sigma_scale, seed,
+                                             frame_idx_dev.data_ptr(), stream_id, id_offset,
+                                             _stream()), "vpf_propagate_dev")
+
+
+def resample_dev(cdf_all, totals, n_local, id_offset, seed, stream_id, frame_idx_dev, state_all,
+                 state_out, idx):
+    _lib.check(_lib.load().vpf_resample_dev(cdf_all.data_ptr(), totals.data_ptr(), totals.numel(),
+                                            n_local, id_offset, seed, stream_id,
+                                            frame_idx_dev.data_ptr(), state_all.data_ptr(),
+                                            state_out.data_ptr(), state_out.stride(0),
+                                            idx.data_ptr(), _stream()), "vpf_resample_dev")
+
+
 def philox_fill(n, id_offset, c1, c2, c3, seed, device="cuda"):
     out = torch.empty((4, n), dtype=torch.int32, device=device)
     _lib.check(_lib.load().vpf_philox_fill(out.data_ptr(), n, id_offset, c1, c2, c3, seed,

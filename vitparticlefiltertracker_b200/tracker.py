@@ -38,7 +38,7 @@ class Tracker:
     def __init__(self, model="vit_base_patch16_224", n_particles=4096, seed=0, device="cuda",
                  dtype=torch.bfloat16, tau=0.1, sigma_pos=None, sigma_vel=None, sigma_scale=0.01,
                  sigma_init=None, state_dict=None, process_group=None, stream_id=0,
-                 encoder=None):
+                 encoder=None, cuda_graph=False):
         if not torch.cuda.is_available():
             raise RuntimeError("Tracker needs a CUDA device: the hot path has no CPU fallback")
         if dtype != torch.bfloat16:
@@ -81,7 +81,13 @@ class Tracker:
         self._stats = torch.zeros((5,), dtype=f64, device=dev)
         self._tbox = torch.empty((1, 4), dtype=f32, device=dev)
         self.frame_idx = -1
-        self.launches_per_step = 0
+        # CUDA-graph mode (single GPU): the whole device side of a step is captured once and
+        # replayed per frame; the frame counter and the resampling uniform then live on the device
+        self.use_graph = bool(cuda_graph) and self.world == 1
+        self._graph = None
+        self._frame_buf = None
+        self._fidx = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.propagated = None
 
     # -- helpers -----------------------------------------------------------------------------
     def _to_device_frame(self, frame):
@@ -115,14 +121,20 @@ class Tracker:
                            self.id_offset)
         self.weights.fill_(1.0 / self.n_global)
         self.frame_idx = 0
+        self._fidx.zero_()
+        self._graph = None
 
     def step(self, frame, _u=None, _emb=None) -> State:
         """One tracked frame.  `_u` (resampling uniform) and `_emb` ([n,D] device embeddings) are
         test hooks that inject oracle quantities; every computation still runs in libvpf."""
         if self.frame_idx < 0:
             raise RuntimeError("call init(frame, bbox) before step(frame)")
+        if self.use_graph and _u is None and _emb is None:
+            return self._step_graph(frame)
         frame = self._to_device_frame(frame)
         self.frame_idx += 1
+        if self.use_graph:
+            self._fidx.fill_(self.frame_idx)      # keep the device counter in step (hook calls)
         t = self.frame_idx
         st = self.particles
         # a3 motion
@@ -164,3 +176,48 @@ class Tracker:
         w = self.w0 * math.exp(sc)
         h = self.h0 * math.exp(sc)
         return State((cx - 0.5 * w, cy - 0.5 * h, w, h), ess, t)
+
+    # -- CUDA-graph path ----------------------------------------------------------------------
+    def _device_step(self):
+        """Device side of one frame with static pointers and no host-supplied scalars."""
+        xch, st = self.xch, self.particles
+        ops.frame_advance(self._fidx)
+        ops.propagate_dev(st, self.sigma_pos, self.sigma_vel, self.sigma_scale, self.seed,
+                          self._fidx, self.stream_id, self.id_offset)
+        ops.crop_state(self._frame_buf, st, self.w0, self.h0, self.patches)
+        self.encoder.forward(self.patches, self.n, self.emb)
+        ops.loglik(self.emb, self.template, self.tau, self.logw, xch.max_local)
+        ops.sumexp(self.logw, xch.max_all, xch.sum_local)
+        total, cdf, _ = xch.local_views()
+        self._stats.zero_()
+        ops.weights(self.logw, xch.max_all, xch.sum_all, st, self.weights, cdf, total, self._stats)
+        ops.resample_dev(cdf, total, self.n, self.id_offset, self.seed, self.stream_id, self._fidx,
+                         st, self._next, self.idx)
+        st.copy_(self._next)                       # keeps every pointer of the graph static
+
+    def _step_graph(self, frame) -> State:
+        if isinstance(frame, np.ndarray):
+            frame = torch.from_numpy(frame)
+        if frame.dtype != torch.uint8 or frame.dim() != 3 or frame.shape[2] != 3:
+            raise ValueError("frame must be uint8 [H, W, 3] RGB")
+        if self._frame_buf is None or self._frame_buf.shape != frame.shape:
+            self._frame_buf = torch.empty(frame.shape, dtype=torch.uint8, device=self.device)
+            self._graph = None
+        self._frame_buf.copy_(frame, non_blocking=True)
+        self.frame_idx += 1
+        if self._graph is None:
+            self._device_step()                    # first frame eagerly: sets kernel attributes,
+            torch.cuda.synchronize()               # builds tensor maps; then capture for replay
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._device_step()
+            self._graph = g
+        else:
+            self._graph.replay()
+        self.last_u = ops.resample_uniform(self.seed, self.frame_idx, self.stream_id)
+        s = self._stats.tolist()
+        sw = s[0]
+        cx, cy, sc = s[2] / sw, s[3] / sw, s[4] / sw
+        w, h = self.w0 * math.exp(sc), self.h0 * math.exp(sc)
+        return State((cx - 0.5 * w, cy - 0.5 * h, w, h), 1.0 / s[1] if s[1] > 0 else 0.0,
+                     self.frame_idx)
