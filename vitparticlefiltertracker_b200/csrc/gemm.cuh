@@ -123,7 +123,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 //           64/128-byte row segments instead of 32 different cache lines).
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const GemmArgs& g,
-                                               uint8_t* slab, int row0, int col, int lane) {
+                                               const CUtensorMap* tmC, uint8_t* slab, int row0,
+                                               int col, int lane) {
   const float4* b4 = reinterpret_cast<const float4*>(g.bias + col);
   if (MODE == kBiasBf16 || MODE == kBiasGeluBf16) {
     // slab rows are 64 B (32 bf16): piece j of row r lives at r*64 + ((j ^ ((r>>1)&3)) << 4)
@@ -145,19 +146,23 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
       uint4 o;
       o.x = pack_bf16(f[0].x, f[0].y); o.y = pack_bf16(f[1].x, f[1].y);
       o.z = pack_bf16(f[2].x, f[2].y); o.w = pack_bf16(f[3].x, f[3].y);
+      if (q == 0) {
+        // the previous chunk's TMA store must have finished reading the slab (it was issued a
+        // whole chunk of tcgen05.ld + math ago, so this does not stall in practice)
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+      }
       *reinterpret_cast<uint4*>(slab + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = o;
     }
+    // slab (32 rows x 64 B, SWIZZLE_64B) -> global through the TMA unit: one instruction, fully
+    // coalesced, rows beyond M clipped by the tensor map
+    fence_proxy_async_smem();
     __syncwarp();
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(g.out);
-    const int p = lane & 3;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = i * 8 + (lane >> 2);
-      const uint4 val = *reinterpret_cast<const uint4*>(slab + r * 64 + ((p ^ ((r >> 1) & 3)) << 4));
-      const int grow = row0 + r;
-      if (grow < g.M)
-        *reinterpret_cast<uint4*>(out + (size_t)grow * g.N + col + p * 8) = val;
+    if (lane == 0) {
+      tma_store_2d(tmC, slab, col, row0);
+      tma_store_commit();
     }
+    return;
   } else {
     // slab rows are 128 B (32 fp32): piece j of row r lives at r*128 + ((j ^ (r&7)) << 4)
 #pragma unroll
@@ -208,7 +213,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
 template <int BLOCK_N, int MODE, int CTAS>
 __global__ void __launch_bounds__((EpiCfg<BLOCK_N, MODE>::kThreads), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmArgs g) {
+                 const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
   using Cfg = GemmCfg<BLOCK_N, CTAS, MODE>;
   using Epi = EpiCfg<BLOCK_N, MODE>;
   constexpr int kStages = Cfg::kStages;
@@ -336,7 +341,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t v[32];
         tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
         tmem_ld_wait();
-        epilogue_chunk<MODE>(v, g, slab, row0, n_blk * BLOCK_N + half * kHalfCols + c * 32, lane);
+        epilogue_chunk<MODE>(v, g, &tmC, slab, row0, n_blk * BLOCK_N + half * kHalfCols + c * 32, lane);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -345,6 +350,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         else mbar_arrive(&tmem_empty[as]);
       }
     }
+    if (MODE <= 1 && lane == 0) tma_store_wait_read<0>();   // smem must outlive the last store
   }
 
   tcgen05_fence_before();

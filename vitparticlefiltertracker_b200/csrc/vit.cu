@@ -69,6 +69,25 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t c
   return VPF_OK;
 }
 
+// bf16 row-major output [rows][cols] for the epilogue's TMA stores: 32 x 32 tiles, 64-byte swizzle
+static int make_store_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return VPF_ERR_CUDA; }
+  if (((uintptr_t)ptr & 15) || (cols * 2) % 16) {
+    set_error("TMA store target must be 16-byte aligned with a 16-byte multiple row pitch");
+    return VPF_ERR_INVALID;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(store) failed: %d", (int)r); return VPF_ERR_CUDA; }
+  return VPF_OK;
+}
+
 static int pick_block_n(int N) {
   if (N % 256 == 0) return 256;
   if (N % 192 == 0) return 192;
@@ -139,7 +158,12 @@ static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VPF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g));
+  CUtensorMap tmC = tmA;                       // modes 2/3 do not use it
+  if (MODE <= 1) {
+    int rc = make_store_map(&tmC, g.out, (uint64_t)g.M, (uint64_t)g.N);
+    if (rc) return rc;
+  }
+  VPF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g));
   return VPF_OK;
 }
 
