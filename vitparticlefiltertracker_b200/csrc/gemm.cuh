@@ -25,7 +25,10 @@ enum GemmMode : int {
   kBiasBf16 = 0,      // out bf16 [M][N] = acc + bias
   kBiasGeluBf16 = 1,  // out bf16 [M][N] = gelu(acc + bias)           (exact-erf GELU)
   kBiasResidualF32 = 2,  // X f32 [M][N] += acc + bias                (in place)
-  kPatchEmbedF32 = 3  // X f32 [(r/196)*197 + 1 + r%196][N] = acc + bias + pos[1 + r%196][N]
+  kPatchEmbedF32 = 3,  // X f32 [(r/196)*197 + 1 + r%196][N] = acc + bias + pos[1 + r%196][N]
+  // internal variant of mode 2, chosen by the launcher for small K (HBM-bound GEMMs such as proj):
+  // the fp32 residual tile is loaded, updated in place and stored entirely by the TMA unit
+  kBiasResidualF32Tma = 4
 };
 
 struct GemmArgs {
@@ -62,12 +65,15 @@ struct GemmCfg {
   static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSlabBytes = 4096;  // per epilogue warp: 32 rows x 128 B transpose slab
-  static constexpr int kEpiBytes = EpiCfg<BLOCK_N, MODE>::kWarps * ((MODE <= 1) ? 2048 : 4096);
-  static constexpr int kStagesMax = (227 * 1024 - kEpiBytes - 1024 - 256) / kStageBytes;
+  // bf16 modes: one 2 KB slab per warp; residual mode: two 4 KB TMA buffers per warp (the fp32
+  // residual tile is loaded, updated in place and stored by the TMA unit); patch embed: 4 KB slab
+  static constexpr int kEpiBytes =
+      EpiCfg<BLOCK_N, MODE>::kWarps * ((MODE <= 1) ? 2048 : (MODE == 4 ? 8192 : 4096));
+  static constexpr int kStagesMax = (227 * 1024 - kEpiBytes - 1024 - 512) / kStageBytes;
   static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
   static constexpr int kTmemCols = (2 * BLOCK_N > 256) ? 512 : 256;
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+      kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 512 /*barriers*/;
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
@@ -227,6 +233,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* epi_bar = full_bar + 32;   // [epilogue warp][2] "residual tile landed" (mode 2)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
@@ -245,6 +252,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], Epi::kWarps * CTAS);   // epilogue warps of every CTA of the group
     }
+    if (MODE == kBiasResidualF32Tma)
+      for (int s = 0; s < 2 * Epi::kWarps; ++s) mbar_init(&epi_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -326,6 +335,78 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int kHalfCols = Epi::kColsPerWarp;
     constexpr int kSlab = (MODE <= 1) ? 2048 : 4096;
     int it = 0;
+    if constexpr (MODE == kBiasResidualF32Tma) {
+      // ---- fp32 residual, in place, entirely through the TMA unit -------------------------
+      // Each warp owns two 4 KB buffers (32 rows x 32 fp32, 128-byte swizzle).  The residual
+      // tile of chunk j+1 is in flight while chunk j is updated in place (x += acc + bias, thread
+      // = row, conflict-free) and handed back to the TMA unit for the store.  No global address
+      // arithmetic, no register staging, rows beyond M clipped / zero-filled by the tensor map.
+      constexpr int kChunks = kHalfCols / 32;
+      uint8_t* xbuf = slabs + (warp - 2) * 8192;
+      uint64_t* xbar = epi_bar + (warp - 2) * 2;
+      uint32_t j = 0;
+      auto issue_load = [&](int tile_, int c_, uint32_t jj) {
+        const int mb = tile_ / n_blocks, nb = tile_ - mb * n_blocks;
+        mbar_arrive_expect_tx(&xbar[jj & 1], 4096);
+        tma_load_2d(xbuf + (jj & 1) * 4096, &tmC, &xbar[jj & 1],
+                    nb * BLOCK_N + half * kHalfCols + c_ * 32,
+                    (mb * CTAS + (int)cta_rank) * kBlockM + quarter * 32);
+      };
+      if (lane == 0 && group < n_tiles) issue_load(group, 0, 0);
+      for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
+        const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_full[as], aphase, 3);
+        tcgen05_fence_after();
+        const int row0 = (m_blk * CTAS + (int)cta_rank) * kBlockM + quarter * 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                               (uint32_t)(as * BLOCK_N + half * kHalfCols);
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c, ++j) {
+          if (lane == 0) {                       // prefetch the next chunk's residual tile
+            int nt = tile, nc = c + 1;
+            if (nc == kChunks) { nt = tile + n_groups; nc = 0; }
+            if (nt < n_tiles) {
+              tma_store_wait_read<0>();          // the other buffer's last store has left smem
+              issue_load(nt, nc, j + 1);
+            }
+          }
+          __syncwarp();
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+          const int col = n_blk * BLOCK_N + half * kHalfCols + c * 32;
+          const float4* b4 = reinterpret_cast<const float4*>(g.bias + col);
+          uint8_t* buf = xbuf + (j & 1) * 4096 + lane * 128;
+          mbar_wait(&xbar[j & 1], (j >> 1) & 1, 4);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4* px = reinterpret_cast<float4*>(buf + ((q ^ (lane & 7)) << 4));
+            const float4 b = __ldg(b4 + q);
+            float4 x = *px;
+            x.x += __uint_as_float(v[q * 4 + 0]) + b.x;
+            x.y += __uint_as_float(v[q * 4 + 1]) + b.y;
+            x.z += __uint_as_float(v[q * 4 + 2]) + b.z;
+            x.w += __uint_as_float(v[q * 4 + 3]) + b.w;
+            *px = x;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, xbuf + (j & 1) * 4096, col, row0);
+            tma_store_commit();
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CTAS == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));
+          else mbar_arrive(&tmem_empty[as]);
+        }
+      }
+      if (lane == 0) tma_store_wait_read<0>();
+    } else {
     for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
       const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
       const int as = it & 1;
@@ -349,6 +430,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (CTAS == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));
         else mbar_arrive(&tmem_empty[as]);
       }
+    }
     }
     if (MODE <= 1 && lane == 0) tma_store_wait_read<0>();   // smem must outlive the last store
   }

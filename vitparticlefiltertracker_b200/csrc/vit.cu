@@ -69,20 +69,24 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t c
   return VPF_OK;
 }
 
-// bf16 row-major output [rows][cols] for the epilogue's TMA stores: 32 x 32 tiles, 64-byte swizzle
-static int make_store_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols) {
+// Row-major [rows][cols] output tile map for the epilogue's TMA traffic, 32 x 32 tiles:
+// bf16 (64-byte rows, 64-byte swizzle) or fp32 (128-byte rows, 128-byte swizzle).
+static int make_store_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols,
+                          bool f32 = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return VPF_ERR_CUDA; }
-  if (((uintptr_t)ptr & 15) || (cols * 2) % 16) {
+  const uint64_t esz = f32 ? 4 : 2;
+  if (((uintptr_t)ptr & 15) || (cols * esz) % 16) {
     set_error("TMA store target must be 16-byte aligned with a 16-byte multiple row pitch");
     return VPF_ERR_INVALID;
   }
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
+  cuuint64_t strides[1] = {cols * esz};
   cuuint32_t box[2] = {32, 32};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(store) failed: %d", (int)r); return VPF_ERR_CUDA; }
   return VPF_OK;
@@ -158,9 +162,9 @@ static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CUtensorMap tmC = tmA;                       // modes 2/3 do not use it
-  if (MODE <= 1) {
-    int rc = make_store_map(&tmC, g.out, (uint64_t)g.M, (uint64_t)g.N);
+  CUtensorMap tmC = tmA;                       // modes 2 / 3 do not use it
+  if (MODE <= 1 || MODE == kBiasResidualF32Tma) {
+    int rc = make_store_map(&tmC, g.out, (uint64_t)g.M, (uint64_t)g.N, MODE == kBiasResidualF32Tma);
     if (rc) return rc;
   }
   VPF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g));
@@ -180,7 +184,11 @@ static int launch_gemm_n(const CUtensorMap& a, const CUtensorMap& b, const GemmA
   switch (mode) {
     case kBiasBf16: return launch_gemm_t<BLOCK_N, kBiasBf16>(a, b, g, s);
     case kBiasGeluBf16: return launch_gemm_t<BLOCK_N, kBiasGeluBf16>(a, b, g, s);
-    case kBiasResidualF32: return launch_gemm_t<BLOCK_N, kBiasResidualF32>(a, b, g, s);
+    case kBiasResidualF32:
+      // small K: the GEMM is bound by the fp32 read-modify-write of the residual -> TMA epilogue
+      // (two tiles in flight per warp); large K: MMA-bound, keep the deeper smem pipeline
+      return g.K <= 1536 ? launch_gemm_t<BLOCK_N, kBiasResidualF32Tma>(a, b, g, s)
+                         : launch_gemm_t<BLOCK_N, kBiasResidualF32>(a, b, g, s);
     case kPatchEmbedF32: return launch_gemm_t<BLOCK_N, kPatchEmbedF32>(a, b, g, s);
   }
   set_error("gemm: unknown epilogue mode %d", mode);
