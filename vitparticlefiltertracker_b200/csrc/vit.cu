@@ -115,6 +115,16 @@ static int make_qkv_map(CUtensorMap* map, const void* ptr, int n_crops, int D, u
   return VPF_OK;
 }
 
+// per-device "already done" flag for per-kernel one-time setup (function attributes are per context)
+static bool first_time_on_device(bool (&done)[32]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 31;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -122,6 +132,7 @@ static int num_sms() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
+    g_num_sms &= ~1;            // CTA pairs: an even number of CTAs
   }
   return g_num_sms;
 }
@@ -141,12 +152,10 @@ static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
                          cudaStream_t s) {
   using Cfg = GemmCfg<BLOCK_N, CTAS, MODE>;
   auto kern = gemm_bf16_kernel<BLOCK_N, MODE, CTAS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[32] = {};
+  if (first_time_on_device(attr_set))
     VPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
-    attr_set = true;
-  }
   const int tiles = ((g.M + kBlockM * CTAS - 1) / (kBlockM * CTAS)) * (g.N / BLOCK_N);
   const int max_groups = num_sms() / CTAS;
   const int groups = tiles < max_groups ? tiles : max_groups;
@@ -286,23 +295,19 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_
                             const CUtensorMap* mq, const CUtensorMap* mkv, cudaStream_t s) {
   const int D = heads * kHeadDim;
   if (attn_use_tc()) {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[32] = {};
+    if (first_time_on_device(attr))
       VPF_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, attn::kSmemBytes));
-      attr = true;
-    }
     const int n_pairs = n_crops * heads;
     const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
     attn::attention_tc_kernel<<<grid, attn::kThreads, attn::kSmemBytes, s>>>(*mq, *mkv, out, n_pairs,
                                                                              heads, D);
   } else {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[32] = {};
+    if (first_time_on_device(attr))
       VPF_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kAttnSmem));
-      attr = true;
-    }
     attention_kernel<<<dim3(heads, n_crops), kAttnThreads, kAttnSmem, s>>>(qkv, out, D);
   }
   VPF_LAUNCH_CHECK();
