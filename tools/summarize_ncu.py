@@ -1,0 +1,76 @@
+"""Turns the raw ncu artefacts brought back in gpurun_out/ into the committed summaries under
+profiles/ (run here, no GPU needed):
+
+    python tools/summarize_ncu.py gpurun_out/launches_r01d.csv gpurun_out/prof_gemm_r01d.ncu-rep
+"""
+import collections
+import csv
+import json
+import subprocess
+import sys
+
+M, D = 4096 * 197, 768
+ALG = {"qkv": (M * D * 2 + 3 * D * D * 2 + M * 3 * D * 2, 2.0 * M * 3 * D * D),
+       "proj": (M * D * 2 + D * D * 2 + 2 * M * D * 4, 2.0 * M * D * D),
+       "fc1": (M * D * 2 + 4 * D * D * 2 + M * 4 * D * 2, 2.0 * M * 4 * D * D),
+       "fc2": (M * 4 * D * 2 + 4 * D * D * 2 + 2 * M * D * 4, 2.0 * M * 4 * D * D)}
+UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+TIME = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr = rows[0]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[1:]:
+        agg[r[ki][:64]][0] += 1
+        agg[r[ki][:64]][1] += float(r[vi].replace(",", ""))
+    tot = sum(v[1] for v in agg.values())
+    lines = [f"{k:64s} n={v[0]:4d} total={v[1] / 1e6:9.3f} ms share={v[1] / tot * 100:5.1f}% "
+             f"avg={v[1] / v[0] / 1e3:9.1f} us" for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])]
+    head = ("ncu --metrics gpu__time_duration.sum --clock-control none -s 385 -c 300, bench.py --steps 2 "
+            "--warmup 3 (1xB200, ViT-B/16, N=4096)\nper-launch times are cold-cache and serialised at "
+            "full clocks: compare SHARES with bench.py's share_of_step\n\n")
+    open("profiles/launches_r01_summary.txt", "w").write(head + "\n".join(lines) + "\n")
+    open("profiles/launches_r01.csv", "w").write(open(path).read())
+    print("\n".join(lines[:8]))
+
+
+def gemm(path):
+    out = subprocess.run(f"ncu -i {path} --page raw --csv", shell=True, capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    g = lambda r, n: float(r[col[n]].replace(",", ""))
+    res = []
+    for r, shape in zip(rows[2:], ["qkv", "proj", "fc1", "fc2", "qkv"]):
+        rd = g(r, "dram__bytes_read.sum") * UNIT[units[col["dram__bytes_read.sum"]]]
+        wr = g(r, "dram__bytes_write.sum") * UNIT[units[col["dram__bytes_write.sum"]]]
+        res.append({"kernel": r[col["Kernel Name"]][:64], "shape": shape,
+                    "duration_ms_under_ncu": g(r, "gpu__time_duration.sum") * TIME[units[col["gpu__time_duration.sum"]]],
+                    "dram_read_bytes": rd, "dram_write_bytes": wr, "traffic_bytes": rd + wr,
+                    "algorithmic_bytes": ALG[shape][0], "flops": ALG[shape][1],
+                    "tensor_pipe_active_pct": g(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                    "sm_clock_ghz": g(r, "sm__cycles_elapsed.avg.per_second"),
+                    "dram_throughput_pct": g(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                    "l2_hit_pct": g(r, "lts__t_sector_hit_rate.pct"),
+                    "issue_active_pct": g(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    "registers": g(r, "launch__registers_per_thread")})
+    fam = {x["shape"]: x for x in res[:4]}
+    summary = {"source": f"ncu --set full --clock-control none, bench.py --steps 2 --warmup 3 (1xB200, ViT-B/16, "
+                         f"N=4096); {path}",
+               "launches": res,
+               "gemm_family_traffic_bytes_per_block": sum(v["traffic_bytes"] for v in fam.values()),
+               "gemm_family_algorithmic_bytes_per_block": sum(v["algorithmic_bytes"] for v in fam.values())}
+    json.dump(summary, open("profiles/ncu_gemm_r01.json", "w"), indent=1)
+    for x in res:
+        print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in x.items()
+               if k in ("shape", "duration_ms_under_ncu", "traffic_bytes", "tensor_pipe_active_pct", "sm_clock_ghz",
+                        "dram_throughput_pct", "registers")})
+
+
+if __name__ == "__main__":
+    launches(sys.argv[1])
+    if len(sys.argv) > 2:
+        gemm(sys.argv[2])
