@@ -293,6 +293,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
+                    help="16-bit operand type of the encoder (fp32 accumulation either way)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -323,7 +325,8 @@ def main():
                            velocity=(3.0, 1.0))
     frames_host = torch.from_numpy(frames).pin_memory()
     frames_dev = torch.from_numpy(frames).to(dev)
-    trk = Tracker(MODEL, n_total, seed=0, device=dev, process_group=pg)
+    op_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    trk = Tracker(MODEL, n_total, seed=0, device=dev, process_group=pg, dtype=op_dtype)
     trk.init(frames_dev[0], gt[0])
 
     def barrier():
@@ -376,7 +379,7 @@ def main():
         line = {                                          #   sumexp, weights, resample
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(n_gpus),
             "frames_per_s": args.steps / (ms_dev / 1e3),
             "step_tflops_per_gpu": trk.n * fl / (ms_step / 1e3) / 1e12,

@@ -32,7 +32,11 @@
 extern "C" {
 #endif
 
-#define VPF_ABI_VERSION 1
+#define VPF_ABI_VERSION 2
+
+/* 16-bit operand type of crops / ViT activations / weights (fp32 accumulation either way) */
+#define VPF_DTYPE_BF16 0
+#define VPF_DTYPE_F16 1
 
 typedef enum {
   VPF_OK = 0,
@@ -49,6 +53,7 @@ typedef struct {
   int32_t depth;     /* L */
   int32_t heads;     /* H, D / H must be 64 */
   int32_t max_crops; /* capacity: largest n_crops of one vpf_vit_forward call */
+  int32_t dtype;     /* VPF_DTYPE_BF16 (default) or VPF_DTYPE_F16 */
 } vpf_vit_config;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -79,11 +84,12 @@ double vpf_resample_uniform(uint64_t seed, uint32_t frame_idx, uint32_t stream_i
 
 /* ---- a4: crop + bilinear resize + normalise + patchify (README.md:7; oracle/crop.py, D3/D4) -
  * frame: uint8 [H][W][3]; boxes come either from the SoA state (w = w0*exp(s), h = h0*exp(s))
- * or from an explicit [n][4] (cx,cy,w,h) array.  out: bf16 [n*196][768], k = c*256+ky*16+kx. */
+ * or from an explicit [n][4] (cx,cy,w,h) array.  out: bf16 or fp16 (`dtype`) [n*196][768],
+ * k = c*256+ky*16+kx.                                                                        */
 int vpf_crop_state(const uint8_t* frame, int H, int W, const float* state, int n, int ld,
-                   float w0, float h0, void* out_bf16, void* stream);
+                   float w0, float h0, void* out16, int dtype, void* stream);
 int vpf_crop_boxes(const uint8_t* frame, int H, int W, const float* boxes, int n,
-                   void* out_bf16, void* stream);
+                   void* out16, int dtype, void* stream);
 
 /* ---- a5: ViT/16 encoder (README.md:7; oracle/vit.py, D1/D2) --------------------------------
  * weights: array of VPF_VIT_N_GLOBAL + 12*depth + 2 device pointers in this order:

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/vpf.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(names)
-    assert lib.vpf_abi_version() == 1
+    assert lib.vpf_abi_version() == 2
 
 
 def test_host_only_entry_points():
@@ -31,7 +31,7 @@ def test_host_only_entry_points():
     lib = _lib.load()
     for seed, t, s in [(0, 1, 0), (123456789012345, 77, 3), (2 ** 64 - 1, 2 ** 32 - 1, 9)]:
         assert lib.vpf_resample_uniform(seed, t, s) == philox_uniform53(t, s, seed)
-    cfg = _lib.VitConfig(768, 12, 12, 4096)
+    cfg = _lib.VitConfig(768, 12, 12, 4096, 0)
     import ctypes as C
     need = lib.vpf_vit_workspace_bytes(C.byref(cfg))
     rows = 4096 * 197
@@ -40,7 +40,7 @@ def test_host_only_entry_points():
     assert lib.vpf_vit_create(None, C.byref(cfg)) == -1
     assert b"null" in lib.vpf_last_error()
     h = C.c_void_p()
-    bad = _lib.VitConfig(100, 12, 12, 16)
+    bad = _lib.VitConfig(100, 12, 12, 16, 0)
     assert lib.vpf_vit_create(C.byref(h), C.byref(bad)) == -1
     assert lib.vpf_vit_create(C.byref(h), C.byref(cfg)) == 0 and h.value
     assert lib.vpf_vit_launches(h) == 2 + 7 * 11 + 10        # CLS-only last block

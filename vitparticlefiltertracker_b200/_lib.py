@@ -13,7 +13,10 @@ _u64, _u32, _size_t = C.c_uint64, C.c_uint32, C.c_size_t
 
 class VitConfig(C.Structure):
     _fields_ = [("dim", C.c_int32), ("depth", C.c_int32), ("heads", C.c_int32),
-                ("max_crops", C.c_int32)]
+                ("max_crops", C.c_int32), ("dtype", C.c_int32)]
+
+
+DTYPE_BF16, DTYPE_F16 = 0, 1
 
 
 # name -> (restype, argtypes); mirrors include/vpf.h one to one
@@ -33,8 +36,8 @@ SIGNATURES = {
     "vpf_normals_fill": (_c_int, [_c_void_p, _c_int, _u32, _u32, _u32, _u64, _c_void_p]),
     "vpf_resample_uniform": (_c_double, [_u64, _u32, _u32]),
     "vpf_crop_state": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_int, _c_float,
-                                _c_float, _c_void_p, _c_void_p]),
-    "vpf_crop_boxes": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p,
+                                _c_float, _c_void_p, _c_int, _c_void_p]),
+    "vpf_crop_boxes": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_int,
                                 _c_void_p]),
     "vpf_vit_create": (_c_int, [C.POINTER(_c_void_p), C.POINTER(VitConfig)]),
     "vpf_vit_destroy": (_c_int, [_c_void_p]),
@@ -79,7 +82,7 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)      # AttributeError here == ABI mismatch with include/vpf.h
         fn.restype = res
         fn.argtypes = args
-    if lib.vpf_abi_version() != 1:
+    if lib.vpf_abi_version() != 2:
         raise RuntimeError("libvpf.so ABI version mismatch")
     _lib = lib
     return lib

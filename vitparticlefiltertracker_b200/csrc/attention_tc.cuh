@@ -61,8 +61,8 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr) 
   d |= (uint64_t)2 << 61;
   return d;
 }
-__host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(int M, int N) {
-  return make_idesc_bf16(M, N) | (1u << 16);     // B operand MN-major
+__host__ __device__ constexpr uint32_t make_idesc_bmn(int M, int N, bool f16) {
+  return make_idesc_16(M, N, f16) | (1u << 16);     // B operand MN-major
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
                                             int c0, int c1, int c2) {
@@ -127,14 +127,12 @@ __device__ __forceinline__ float2 fadd2v(float2 a, float2 b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
   return *reinterpret_cast<float2*>(&rd);
 }
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
+__device__ __forceinline__ uint32_t pack2(float a, float b, bool f16) { return pack16x2(a, b, f16); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                    __nv_bfloat16* __restrict__ out, int n_pairs, int heads, int D) {
+                    __nv_bfloat16* __restrict__ out, int n_pairs, int heads, int D, int f16_) {
+  const bool f16 = f16_ != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -194,8 +192,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, kKeys);
-      constexpr uint32_t idesc_o = make_idesc_bf16_bmn(128, kD);
+      const uint32_t idesc_s = make_idesc_16(128, kKeys, f16);
+      const uint32_t idesc_o = make_idesc_bmn(128, kD, f16);
       const int units = 2 * my_pairs;
       auto issue_s = [&](int u) {
         const int ip = u >> 1, b = u & 1, qs = u & 3, ks = ip & 1;
@@ -287,7 +285,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                                     c2, nmc2);
             const float2 p = make_float2(ex2(a.x), ex2(a.y));
             l2 = fadd2v(l2, p);
-            pk[j] = pack2(p.x, p.y);
+            pk[j] = pack2(p.x, p.y, f16);
           }
           tmem_st_32x16(tbuf + (uint32_t)(ch * 16), pk);
         };
@@ -311,7 +309,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const float p0 = (k0 < kT) ? ex2(fmaf(__uint_as_float(va[2 * j]), c, nmc2.x)) : 0.f;
             const float p1 = (k0 + 1 < kT) ? ex2(fmaf(__uint_as_float(va[2 * j + 1]), c, nmc2.x)) : 0.f;
             l2.x += p0; l2.y += p1;
-            pk[j] = pack2(p0, p1);
+            pk[j] = pack2(p0, p1, f16);
           }
           tmem_st_32x8(tbuf + 96u, pk);
         }
@@ -334,10 +332,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 o;
-            o.x = pack2(__uint_as_float(v[q * 8 + 0]) * inv_l, __uint_as_float(v[q * 8 + 1]) * inv_l);
-            o.y = pack2(__uint_as_float(v[q * 8 + 2]) * inv_l, __uint_as_float(v[q * 8 + 3]) * inv_l);
-            o.z = pack2(__uint_as_float(v[q * 8 + 4]) * inv_l, __uint_as_float(v[q * 8 + 5]) * inv_l);
-            o.w = pack2(__uint_as_float(v[q * 8 + 6]) * inv_l, __uint_as_float(v[q * 8 + 7]) * inv_l);
+            o.x = pack2(__uint_as_float(v[q * 8 + 0]) * inv_l, __uint_as_float(v[q * 8 + 1]) * inv_l, f16);
+            o.y = pack2(__uint_as_float(v[q * 8 + 2]) * inv_l, __uint_as_float(v[q * 8 + 3]) * inv_l, f16);
+            o.z = pack2(__uint_as_float(v[q * 8 + 4]) * inv_l, __uint_as_float(v[q * 8 + 5]) * inv_l, f16);
+            o.w = pack2(__uint_as_float(v[q * 8 + 6]) * inv_l, __uint_as_float(v[q * 8 + 7]) * inv_l, f16);
             const int chunk = hlf * 4 + q;
             *reinterpret_cast<uint4*>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
           }

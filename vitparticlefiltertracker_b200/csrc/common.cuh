@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -47,6 +48,23 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// 16-bit operand type of the encoder: bf16 (default) or fp16 (same tensor-core rate and bytes,
+// 3 more mantissa bits, less range) -- a run-time, warp-uniform flag.
+__device__ __forceinline__ uint32_t pack16x2(float a, float b, bool f16) {
+  if (f16) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack16x2(uint32_t v, bool f16) {
+  if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+}
+__device__ __forceinline__ uint16_t pack16(float a, bool f16) {
+  if (f16) { __half h = __float2half_rn(a); return *reinterpret_cast<uint16_t*>(&h); }
+  __nv_bfloat16 h = __float2bfloat16_rn(a);
+  return *reinterpret_cast<uint16_t*>(&h);
 }
 
 // ---- Philox4x32-10 (Random123 constants), shared by host and device ----------------------

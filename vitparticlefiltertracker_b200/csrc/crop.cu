@@ -40,7 +40,7 @@ template <bool kFromState>
 __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ frame, int H, int W,
                                                     const float* __restrict__ src, int n, int ld,
                                                     float w0, float h0,
-                                                    __nv_bfloat16* __restrict__ out) {
+                                                    __nv_bfloat16* __restrict__ out, bool f16) {
   __shared__ uint32_t stage[kStageWords];
   __shared__ float s_fx[kCrop];
   __shared__ int s_x0[kCrop];
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ f
       off0 = (long long)y0 * W * 3;
       off1 = (long long)y1 * W * 3;
     }
-    __align__(16) __nv_bfloat16 v[3][8];
+    __align__(16) uint16_t v[3][8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int j = px * kPatch + kx0 + e;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ f
         float top = __fadd_rn(__fmul_rn(gx, p00), __fmul_rn(fx, p01));
         float bot = __fadd_rn(__fmul_rn(gx, p10), __fmul_rn(fx, p11));
         float val = __fadd_rn(__fmul_rn(gy, top), __fmul_rn(fy, bot));
-        v[c][e] = __float2bfloat16_rn(__fsub_rn(__fmul_rn(val, c255), 1.0f));
+        v[c][e] = pack16(__fsub_rn(__fmul_rn(val, c255), 1.0f), f16);
       }
     }
     __nv_bfloat16* dst = out + ((size_t)crop * kPatches + p) * kPatchK + ky * kPatch + kx0;
@@ -152,23 +152,25 @@ using namespace vpf;
 extern "C" {
 
 int vpf_crop_state(const uint8_t* frame, int H, int W, const float* state, int n, int ld,
-                   float w0, float h0, void* out_bf16, void* stream) {
+                   float w0, float h0, void* out_bf16, int dtype, void* stream) {
+  VPF_REQUIRE(dtype == VPF_DTYPE_BF16 || dtype == VPF_DTYPE_F16, "vpf_crop_state: bad dtype");
   VPF_REQUIRE(frame && state && out_bf16 && H > 0 && W > 0 && n > 0 && ld >= n,
               "vpf_crop_state: bad arguments");
   VPF_REQUIRE(((uintptr_t)out_bf16 & 15) == 0, "vpf_crop_state: out must be 16-byte aligned");
   crop_kernel<true><<<dim3(n, kSplit), 256, 0, (cudaStream_t)stream>>>(
-      frame, H, W, state, n, ld, w0, h0, (__nv_bfloat16*)out_bf16);
+      frame, H, W, state, n, ld, w0, h0, (__nv_bfloat16*)out_bf16, dtype == VPF_DTYPE_F16);
   VPF_LAUNCH_CHECK();
   return VPF_OK;
 }
 
 int vpf_crop_boxes(const uint8_t* frame, int H, int W, const float* boxes, int n, void* out_bf16,
-                   void* stream) {
+                   int dtype, void* stream) {
+  VPF_REQUIRE(dtype == VPF_DTYPE_BF16 || dtype == VPF_DTYPE_F16, "vpf_crop_boxes: bad dtype");
   VPF_REQUIRE(frame && boxes && out_bf16 && H > 0 && W > 0 && n > 0,
               "vpf_crop_boxes: bad arguments");
   VPF_REQUIRE(((uintptr_t)out_bf16 & 15) == 0, "vpf_crop_boxes: out must be 16-byte aligned");
   crop_kernel<false><<<dim3(n, kSplit), 256, 0, (cudaStream_t)stream>>>(
-      frame, H, W, boxes, n, 0, 1.f, 1.f, (__nv_bfloat16*)out_bf16);
+      frame, H, W, boxes, n, 0, 1.f, 1.f, (__nv_bfloat16*)out_bf16, dtype == VPF_DTYPE_F16);
   VPF_LAUNCH_CHECK();
   return VPF_OK;
 }

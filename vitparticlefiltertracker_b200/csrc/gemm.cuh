@@ -36,6 +36,7 @@ struct GemmArgs {
   const float* bias;
   void* out;
   const float* pos;
+  int f16 = 0;   // 16-bit operand / output type: 0 = bf16, 1 = fp16
 };
 
 static constexpr int kBlockM = 128;
@@ -150,8 +151,9 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
         for (int e = 0; e < 4; ++e) f[e] = gelu_erf2(f[e]);
       }
       uint4 o;
-      o.x = pack_bf16(f[0].x, f[0].y); o.y = pack_bf16(f[1].x, f[1].y);
-      o.z = pack_bf16(f[2].x, f[2].y); o.w = pack_bf16(f[3].x, f[3].y);
+      const bool f16 = g.f16 != 0;
+      o.x = pack16x2(f[0].x, f[0].y, f16); o.y = pack16x2(f[1].x, f[1].y, f16);
+      o.z = pack16x2(f[2].x, f[2].y, f16); o.w = pack16x2(f[3].x, f[3].y, f16);
       if (q == 0) {
         // the previous chunk's TMA store must have finished reading the slab (it was issued a
         // whole chunk of tcgen05.ld + math ago, so this does not stall in practice)
@@ -295,7 +297,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CTAS, BLOCK_N);
+      const uint32_t idesc = make_idesc_16(kBlockM * CTAS, BLOCK_N, g.f16 != 0);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {

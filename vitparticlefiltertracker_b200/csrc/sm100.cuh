@@ -233,5 +233,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
+// same with fp16 operands (A / B format code 0 instead of 1)
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, bool f16) {
+  return f16 ? ((1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24))
+             : make_idesc_bf16(M, N);
+}
 
 }  // namespace vpf

@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                          size_t row_stride,
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta,
-                                                         OutT* __restrict__ out, int rows, int D) {
+                                                         OutT* __restrict__ out, int rows, int D,
+                                                         bool f16 = false) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -262,8 +263,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       float o3 = (v[i].w - mean) * rstd * g.w + b.w;
       if (sizeof(OutT) == 2) {
         uint2 p;
-        p.x = pack_bf16(o0, o1);
-        p.y = pack_bf16(o2, o3);
+        p.x = pack16x2(o0, o1, f16);
+        p.y = pack16x2(o2, o3, f16);
         reinterpret_cast<uint2*>(out + (size_t)row * D)[idx] = p;
       } else {
         reinterpret_cast<float4*>(out + (size_t)row * D)[idx] = make_float4(o0, o1, o2, o3);
@@ -292,7 +293,8 @@ static bool attn_use_tc() {
 }
 
 static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_crops, int heads,
-                            const CUtensorMap* mq, const CUtensorMap* mkv, cudaStream_t s) {
+                            const CUtensorMap* mq, const CUtensorMap* mkv, cudaStream_t s,
+                            int f16 = 0) {
   const int D = heads * kHeadDim;
   if (attn_use_tc()) {
     static bool attr[32] = {};
@@ -302,8 +304,9 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_
     const int n_pairs = n_crops * heads;
     const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
     attn::attention_tc_kernel<<<grid, attn::kThreads, attn::kSmemBytes, s>>>(*mq, *mkv, out, n_pairs,
-                                                                             heads, D);
+                                                                             heads, D, f16);
   } else {
+    if (f16) { set_error("VPF_ATTN=mma supports bf16 operands only"); return VPF_ERR_UNSUPPORTED; }
     static bool attr[32] = {};
     if (first_time_on_device(attr))
       VPF_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -332,7 +335,7 @@ __global__ void gather_cls_kernel(const float* __restrict__ X, float* __restrict
 __global__ void __launch_bounds__(256) cls_attention_kernel(const __nv_bfloat16* __restrict__ q,
                                                             const __nv_bfloat16* __restrict__ kv,
                                                             __nv_bfloat16* __restrict__ o,
-                                                            int n_pairs, int heads) {
+                                                            int n_pairs, int heads, bool f16) {
   const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (pair >= n_pairs) return;
@@ -344,10 +347,10 @@ __global__ void __launch_bounds__(256) cls_attention_kernel(const __nv_bfloat16*
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       uint4 t = __ldg(q4 + i);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+      const uint32_t* h = reinterpret_cast<const uint32_t*>(&t);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float2 f = __bfloat1622float2(h[j]);
+        float2 f = unpack16x2(h[j], f16);
         qf[i * 8 + j * 2] = f.x; qf[i * 8 + j * 2 + 1] = f.y;
       }
     }
@@ -366,10 +369,10 @@ __global__ void __launch_bounds__(256) cls_attention_kernel(const __nv_bfloat16*
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         uint4 t = __ldg(k4 + u);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+        const uint32_t* h = reinterpret_cast<const uint32_t*>(&t);
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          float2 f = __bfloat1622float2(h[w]);
+          float2 f = unpack16x2(h[w], f16);
           acc = fmaf(qf[u * 8 + w * 2], f.x, acc);
           acc = fmaf(qf[u * 8 + w * 2 + 1], f.y, acc);
         }
@@ -396,15 +399,15 @@ __global__ void __launch_bounds__(256) cls_attention_kernel(const __nv_bfloat16*
       const int j = i * 32 + jj;
       const float p = __shfl_sync(0xffffffffu, sc[i], jj);
       if (j < kTokens) {
-        float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vbase + (size_t)j * 2 * D));
+        float2 f = unpack16x2(*reinterpret_cast<const uint32_t*>(vbase + (size_t)j * 2 * D), f16);
         o0 = fmaf(p, f.x, o0);
         o1 = fmaf(p, f.y, o1);
       }
     }
   }
   const float inv = 1.0f / l;
-  *reinterpret_cast<__nv_bfloat162*>(o + (size_t)crop * D + head * kHeadDim + 2 * lane) =
-      __floats2bfloat162_rn(o0 * inv, o1 * inv);
+  *reinterpret_cast<uint32_t*>(o + (size_t)crop * D + head * kHeadDim + 2 * lane) =
+      pack16x2(o0 * inv, o1 * inv, f16);
 }
 
 struct LayerW {
@@ -450,6 +453,8 @@ int vpf_vit_create(vpf_vit** out, const vpf_vit_config* cfg) {
   VPF_REQUIRE(cfg->dim > 0 && cfg->dim % 64 == 0 && cfg->dim <= 1024 && cfg->depth > 0 &&
                   cfg->heads > 0 && cfg->heads * 64 == cfg->dim && cfg->max_crops > 0,
               "vpf_vit_create: need dim = 64*heads <= 1024, depth > 0, max_crops > 0");
+  VPF_REQUIRE(cfg->dtype == VPF_DTYPE_BF16 || cfg->dtype == VPF_DTYPE_F16,
+              "vpf_vit_create: dtype must be VPF_DTYPE_BF16 or VPF_DTYPE_F16");
   if (!pick_block_n(cfg->dim) || !pick_block_n(3 * cfg->dim)) {
     set_error("vpf_vit_create: dim %d unsupported (dim and 3*dim must be multiples of 128)", cfg->dim);
     return VPF_ERR_UNSUPPORTED;
@@ -538,27 +543,32 @@ int vpf_vit_launches(const vpf_vit* h) {
 // One full encoder block on every token row.
 static int run_block(vpf_vit* h, const LayerW& w, int n, cudaStream_t s) {
   const int D = h->cfg.dim, H = h->cfg.heads, M = n * kTokens;
+  const int f16 = h->cfg.dtype == VPF_DTYPE_F16;
   const int ln_blocks = (M + 7) / 8;
   int rc;
-  layernorm_kernel<__nv_bfloat16><<<ln_blocks, 256, 0, s>>>(h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D);
+  layernorm_kernel<__nv_bfloat16><<<ln_blocks, 256, 0, s>>>(h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0);
   VPF_LAUNCH_CHECK();
   {
     GemmArgs g{M, 3 * D, D, w.qkv_b, h->big, nullptr};
+      g.f16 = f16;
     if ((rc = launch_gemm(h->a_xn, w.m_qkv, g, kBiasBf16, s))) return rc;
   }
-  if ((rc = launch_attention(h->big, h->Xn, n, H, &h->a_q, &h->a_kv, s))) return rc;
+  if ((rc = launch_attention(h->big, h->Xn, n, H, &h->a_q, &h->a_kv, s, f16))) return rc;
   {
     GemmArgs g{M, D, D, w.proj_b, h->X, nullptr};
+      g.f16 = f16;
     if ((rc = launch_gemm(h->a_xn, w.m_proj, g, kBiasResidualF32, s))) return rc;
   }
-  layernorm_kernel<__nv_bfloat16><<<ln_blocks, 256, 0, s>>>(h->X, D, w.ln2_g, w.ln2_b, h->Xn, M, D);
+  layernorm_kernel<__nv_bfloat16><<<ln_blocks, 256, 0, s>>>(h->X, D, w.ln2_g, w.ln2_b, h->Xn, M, D, f16 != 0);
   VPF_LAUNCH_CHECK();
   {
     GemmArgs g{M, 4 * D, D, w.fc1_b, h->big, nullptr};
+      g.f16 = f16;
     if ((rc = launch_gemm(h->a_xn, w.m_fc1, g, kBiasGeluBf16, s))) return rc;
   }
   {
     GemmArgs g{M, D, 4 * D, w.fc2_b, h->X, nullptr};
+      g.f16 = f16;
     if ((rc = launch_gemm(h->a_big, w.m_fc2, g, kBiasResidualF32, s))) return rc;
   }
   return VPF_OK;
@@ -584,34 +594,40 @@ static ClsBufs cls_bufs(const vpf_vit* h, int n) {
 
 static int run_last_block_cls(vpf_vit* h, const LayerW& w, int n, float* emb, cudaStream_t s) {
   const int D = h->cfg.dim, H = h->cfg.heads, M = n * kTokens;
+  const int f16 = h->cfg.dtype == VPF_DTYPE_F16;
   const ClsBufs c = cls_bufs(h, n);
   int rc;
-  layernorm_kernel<__nv_bfloat16><<<(M + 7) / 8, 256, 0, s>>>(h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D);
+  layernorm_kernel<__nv_bfloat16><<<(M + 7) / 8, 256, 0, s>>>(h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0);
   VPF_LAUNCH_CHECK();
   {  // K, V for every token: rows [D, 3D) of the fused qkv weight
     GemmArgs g{M, 2 * D, D, w.qkv_b + D, h->big, nullptr};
+      g.f16 = f16;
     if ((rc = launch_gemm(h->a_xn, h->m_kv_last, g, kBiasBf16, s))) return rc;
   }
   {  // Q for the CLS rows only (strided view of Xn)
     GemmArgs g{n, D, D, w.qkv_b, c.q, nullptr};
+      g.f16 = f16;
     if ((rc = launch_gemm(h->a_xn_cls, h->m_q_last, g, kBiasBf16, s))) return rc;
   }
-  cls_attention_kernel<<<(n * H + 7) / 8, 256, 0, s>>>(c.q, h->big, c.o, n * H, H);
+  cls_attention_kernel<<<(n * H + 7) / 8, 256, 0, s>>>(c.q, h->big, c.o, n * H, H, f16 != 0);
   VPF_LAUNCH_CHECK();
   gather_cls_kernel<<<(n * (D / 4) + 255) / 256, 256, 0, s>>>(h->X, c.xc, n, D);
   VPF_LAUNCH_CHECK();
   {
     GemmArgs g{n, D, D, w.proj_b, c.xc, nullptr};
+      g.f16 = f16;
     if ((rc = launch_gemm(h->a_ocls, w.m_proj, g, kBiasResidualF32, s))) return rc;
   }
-  layernorm_kernel<__nv_bfloat16><<<(n + 7) / 8, 256, 0, s>>>(c.xc, D, w.ln2_g, w.ln2_b, c.xn, n, D);
+  layernorm_kernel<__nv_bfloat16><<<(n + 7) / 8, 256, 0, s>>>(c.xc, D, w.ln2_g, w.ln2_b, c.xn, n, D, f16 != 0);
   VPF_LAUNCH_CHECK();
   {
     GemmArgs g{n, 4 * D, D, w.fc1_b, c.hc, nullptr};
+      g.f16 = f16;
     if ((rc = launch_gemm(h->a_xnc, w.m_fc1, g, kBiasGeluBf16, s))) return rc;
   }
   {
     GemmArgs g{n, D, 4 * D, w.fc2_b, c.xc, nullptr};
+      g.f16 = f16;
     if ((rc = launch_gemm(h->a_hc, w.m_fc2, g, kBiasResidualF32, s))) return rc;
   }
   layernorm_kernel<float><<<(n + 7) / 8, 256, 0, s>>>(c.xc, D, h->norm_g, h->norm_b, emb, n, D);
@@ -650,6 +666,7 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
   VPF_LAUNCH_CHECK();
   {
     GemmArgs g{M0, D, 768, h->patch_b, h->X, h->pos};
+    g.f16 = h->cfg.dtype == VPF_DTYPE_F16;
     if ((rc = launch_gemm(h->a_patches, h->m_patch, g, kPatchEmbedF32, s))) return rc;
   }
   const int full_blocks = h->cls_prune ? L - 1 : L;

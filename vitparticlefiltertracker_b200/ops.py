@@ -20,6 +20,14 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _dtype_code(dtype) -> int:
+    if dtype == torch.bfloat16:
+        return _lib.DTYPE_BF16
+    if dtype == torch.float16:
+        return _lib.DTYPE_F16
+    raise ValueError("the encoder's 16-bit operand type must be torch.bfloat16 or torch.float16")
+
+
 def _dev(t: torch.Tensor, dtype) -> torch.Tensor:
     assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), (t.device, t.dtype, dtype)
     return t
@@ -83,28 +91,29 @@ def resample_uniform(seed, frame_idx, stream_id=0) -> float:
 
 
 # ---- crop --------------------------------------------------------------------------------------
-def crop_state(frame, state, w0, h0, out=None):
+def crop_state(frame, state, w0, h0, out=None, dtype=torch.bfloat16):
     _dev(frame, torch.uint8)
     _dev(state, torch.float32)
     H, W, _ = frame.shape
     n = state.shape[1]
     if out is None:
-        out = torch.empty((n * N_PATCH, PATCH_K), dtype=torch.bfloat16, device=frame.device)
+        out = torch.empty((n * N_PATCH, PATCH_K), dtype=dtype, device=frame.device)
     _lib.check(_lib.load().vpf_crop_state(frame.data_ptr(), H, W, state.data_ptr(), n,
-                                          state.stride(0), w0, h0, out.data_ptr(), _stream()),
-               "vpf_crop_state")
+                                          state.stride(0), w0, h0, out.data_ptr(),
+                                          _dtype_code(out.dtype), _stream()), "vpf_crop_state")
     return out
 
 
-def crop_boxes(frame, boxes, out=None):
+def crop_boxes(frame, boxes, out=None, dtype=torch.bfloat16):
     _dev(frame, torch.uint8)
     _dev(boxes, torch.float32)
     H, W, _ = frame.shape
     n = boxes.shape[0]
     if out is None:
-        out = torch.empty((n * N_PATCH, PATCH_K), dtype=torch.bfloat16, device=frame.device)
+        out = torch.empty((n * N_PATCH, PATCH_K), dtype=dtype, device=frame.device)
     _lib.check(_lib.load().vpf_crop_boxes(frame.data_ptr(), H, W, boxes.data_ptr(), n,
-                                          out.data_ptr(), _stream()), "vpf_crop_boxes")
+                                          out.data_ptr(), _dtype_code(out.dtype), _stream()),
+               "vpf_crop_boxes")
     return out
 
 
@@ -175,11 +184,16 @@ def resample(cdf_all, totals, n_local, id_offset, u, state_all, state_out, idx):
 class VitEncoder:
     """Owns the opaque vpf_vit handle, the packed device weights and the workspace tensor."""
 
-    def __init__(self, dim, depth, heads, max_crops, packed_weights, device="cuda"):
+    def __init__(self, dim, depth, heads, max_crops, packed_weights, device="cuda",
+                 dtype=torch.bfloat16):
         lib = _lib.load()
         self._lib = lib
         self.dim, self.depth, self.heads, self.max_crops = dim, depth, heads, max_crops
-        self.cfg = _lib.VitConfig(dim, depth, heads, max_crops)
+        self.dtype = dtype
+        wd = {t.dtype for t in packed_weights if t.dtype in (torch.bfloat16, torch.float16)}
+        if wd != {dtype}:
+            raise ValueError(f"packed GEMM weights are {wd}, encoder operand type is {dtype}")
+        self.cfg = _lib.VitConfig(dim, depth, heads, max_crops, _dtype_code(dtype))
         self._h = C.c_void_p()
         _lib.check(lib.vpf_vit_create(C.byref(self._h), C.byref(self.cfg)), "vpf_vit_create")
         self.weights = [t.to(device).contiguous() for t in packed_weights]   # keep alive
@@ -193,7 +207,7 @@ class VitEncoder:
         self.launches = lib.vpf_vit_launches(self._h)
 
     def forward(self, patches, n_crops, emb=None):
-        assert patches.is_cuda and patches.dtype == torch.bfloat16 and patches.is_contiguous()
+        assert patches.is_cuda and patches.dtype == self.dtype and patches.is_contiguous()
         if emb is None:
             emb = torch.empty((n_crops, self.dim), dtype=torch.float32, device=patches.device)
         _lib.check(self._lib.vpf_vit_forward(self._h, patches.data_ptr(), n_crops, emb.data_ptr(),

@@ -41,8 +41,10 @@ class Tracker:
                  encoder=None, cuda_graph=False):
         if not torch.cuda.is_available():
             raise RuntimeError("Tracker needs a CUDA device: the hot path has no CPU fallback")
-        if dtype != torch.bfloat16:
-            raise ValueError("the sm_100a ViT path computes in bf16 with fp32 accumulation")
+        if dtype not in (torch.bfloat16, torch.float16):
+            raise ValueError("the sm_100a ViT path takes bf16 (default) or fp16 operands, "
+                             "fp32 accumulation")
+        self.dtype = dtype
         if model not in VIT_CONFIGS:
             raise ValueError(f"unknown model {model!r}; choose from {sorted(VIT_CONFIGS)}")
         self.model = model
@@ -64,15 +66,16 @@ class Tracker:
         if encoder is None:
             sd = state_dict if state_dict is not None else init_state_dict(model)
             encoder = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], self.n,
-                                     pack_for_device(model, sd), device=self.device)
-        assert encoder.max_crops >= self.n
+                                     pack_for_device(model, sd, dtype), device=self.device,
+                                     dtype=dtype)
+        assert encoder.max_crops >= self.n and encoder.dtype == dtype
         self.encoder = encoder
         dev, n, R = self.device, self.n, self.world
         f32, f64 = torch.float32, torch.float64
         self.particles = torch.zeros((6, n), dtype=f32, device=dev)
         self._next = torch.zeros((6, n), dtype=f32, device=dev)
         self.weights = torch.full((n,), 1.0 / self.n_global, dtype=f32, device=dev)
-        self.patches = torch.empty((n * ops.N_PATCH, ops.PATCH_K), dtype=torch.bfloat16, device=dev)
+        self.patches = torch.empty((n * ops.N_PATCH, ops.PATCH_K), dtype=dtype, device=dev)
         self.emb = torch.empty((n, self.dim), dtype=f32, device=dev)
         self.logw = torch.empty((n,), dtype=f32, device=dev)
         self.idx = torch.empty((n,), dtype=torch.int32, device=dev)
@@ -113,7 +116,7 @@ class Tracker:
         self.sigma_scale = float(np.float32(ss))
         self.sigma_init = float(np.float32(0.1 * scale if si is None else si))
         self._tbox.copy_(torch.tensor([[x + 0.5 * w, y + 0.5 * h, w, h]], dtype=torch.float32))
-        tp = ops.crop_boxes(frame, self._tbox)
+        tp = ops.crop_boxes(frame, self._tbox, dtype=self.dtype)
         self.encoder.forward(tp, 1, self.template.view(1, -1))
         cx = float(np.float32(np.float32(x) + np.float32(0.5) * np.float32(w)))
         cy = float(np.float32(np.float32(y) + np.float32(0.5) * np.float32(h)))

@@ -63,13 +63,13 @@ def init_state_dict(model: str, seed: int = WEIGHT_SEED) -> dict:
     return sd
 
 
-def pack_for_device(model: str, sd: dict) -> list:
-    """timm state_dict -> list of CPU tensors in libvpf pointer order: GEMM weights bf16 [out][in]
-    (the K-major B operand), everything else fp32."""
+def pack_for_device(model: str, sd: dict, dtype=torch.bfloat16) -> list:
+    """timm state_dict -> list of CPU tensors in libvpf pointer order: GEMM weights in the 16-bit
+    operand type (`dtype`: bf16 or fp16) [out][in] (the K-major B operand), everything else fp32."""
     c = VIT_CONFIGS[model]
     d, depth = c["dim"], c["depth"]
     f32 = lambda t: t.detach().to(torch.float32).contiguous()
-    bf = lambda t: t.detach().to(torch.float32).to(torch.bfloat16).contiguous()
+    bf = lambda t: t.detach().to(torch.float32).to(dtype).contiguous()
     out = [bf(sd["patch_embed.proj.weight"].reshape(d, 768)), f32(sd["patch_embed.proj.bias"]),
            f32(sd["cls_token"].reshape(d)), f32(sd["pos_embed"].reshape(TOKENS, d))]
     for i in range(depth):
