@@ -95,3 +95,20 @@ def test_cuda_graph_mode_is_bit_identical_to_eager():
         assert torch.equal(eager.idx, graph.idx) and torch.equal(eager.weights, graph.weights)
         assert a.bbox == b.bbox and a.ess == b.ess
     assert graph._graph is not None
+
+
+def test_checkpoint_resume_reproduces_the_trajectory():
+    from vitparticlefiltertracker_b200 import Tracker
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+    cuda()
+    frames, gt = make_clip("box", 224, 224, 7, seed=2, target=(48, 48))
+    a = Tracker("vit_tiny_patch16_224", 128, seed=3)
+    a.init(frames[0], gt[0])
+    for t in range(1, 4):
+        a.step(frames[t])
+    ckpt = a.state_dict()
+    ref = [a.step(frames[t]) for t in range(4, 7)]
+    b = Tracker("vit_tiny_patch16_224", 128, seed=99, encoder=a.encoder)   # shares the weights
+    b.load_state_dict(ckpt)
+    got = [b.step(frames[t]) for t in range(4, 7)]
+    assert got == ref and torch.equal(a.particles, b.particles)

@@ -180,6 +180,32 @@ class Tracker:
         h = self.h0 * math.exp(sc)
         return State((cx - 0.5 * w, cy - 0.5 * h, w, h), ess, t)
 
+    # -- checkpoint / resume -------------------------------------------------------------------
+    def state_dict(self) -> dict:
+        """Everything needed to resume this stream: particle set, template, frame counter and
+        the scalars fixed by init() (device tensors are cloned)."""
+        if self.frame_idx < 0:
+            raise RuntimeError("nothing to save before init()")
+        return {"particles": self.particles.clone(), "weights": self.weights.clone(),
+                "template": self.template.clone(), "frame_idx": self.frame_idx,
+                "seed": self.seed, "stream_id": self.stream_id, "w0": self.w0, "h0": self.h0,
+                "sigmas": (self.sigma_pos, self.sigma_vel, self.sigma_scale, self.sigma_init),
+                "model": self.model, "n_particles": self.n_global, "rank": self.rank,
+                "world": self.world}
+
+    def load_state_dict(self, sd: dict) -> None:
+        if (sd["model"], sd["n_particles"], sd["rank"], sd["world"]) != \
+                (self.model, self.n_global, self.rank, self.world):
+            raise ValueError("checkpoint was taken with a different model / particle count / sharding")
+        self.particles.copy_(sd["particles"])
+        self.weights.copy_(sd["weights"])
+        self.template.copy_(sd["template"])
+        self.frame_idx, self.seed, self.stream_id = sd["frame_idx"], sd["seed"], sd["stream_id"]
+        self.w0, self.h0 = sd["w0"], sd["h0"]
+        self.sigma_pos, self.sigma_vel, self.sigma_scale, self.sigma_init = sd["sigmas"]
+        self._fidx.fill_(self.frame_idx)
+        self._graph = None
+
     # -- CUDA-graph path ----------------------------------------------------------------------
     def _device_step(self):
         """Device side of one frame with static pointers and no host-supplied scalars."""
