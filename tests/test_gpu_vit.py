@@ -145,3 +145,33 @@ def test_cls_only_last_block_matches_full_last_block(monkeypatch):
     assert full.launches == 2 + 7 * 12 + 1 and pruned.launches == 2 + 7 * 11 + 10
     b = full.forward(patches, n).cpu()
     assert _rel(a, b) < 2e-3, _rel(a, b)
+
+
+def test_vit_forward_with_nontrivial_biases_and_layernorm_params():
+    """The seeded init has zero biases and unit LayerNorm gains; a real (timm) checkpoint does
+    not.  Randomise every bias / gamma / beta / cls token so that each fused term is exercised
+    end to end, through the same state_dict= path a pretrained checkpoint would take."""
+    from vitparticlefiltertracker_b200 import ops, pack_for_device
+    dev = cuda()
+    model, n = "vit_tiny_patch16_224", 7
+    cfg = VIT_CONFIGS[model]
+    g = torch.Generator().manual_seed(3)
+    sd = {}
+    for k, v in init_vit_weights(model).items():
+        if k.endswith("bias"):
+            sd[k] = torch.randn(v.shape, generator=g) * 0.1
+        elif "norm" in k and k.endswith("weight"):
+            sd[k] = 1 + torch.randn(v.shape, generator=g) * 0.2
+        elif k == "cls_token":
+            sd[k] = torch.randn(v.shape, generator=g) * 0.05
+        else:
+            sd[k] = v * 2.0
+    crops = torch.randn(n, 3, 224, 224, generator=g).clamp(-1, 1)
+    want = torch.from_numpy(vit_forward(crops.numpy(), sd, model))
+    from oracle.crop import patchify
+    enc = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], n, pack_for_device(model, sd), dev)
+    got = enc.forward(torch.from_numpy(patchify(crops.numpy())).to(torch.bfloat16).to(dev), n).cpu()
+    rel = _rel(got, want)
+    cos = torch.nn.functional.cosine_similarity(got, want, dim=1)
+    print(f"randomised checkpoint: rel-L2 {rel:.3e}, min cos {cos.min():.6f}")
+    assert rel < 1.5e-2 and cos.min() > 1 - 1e-3
