@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VPF_ABI_VERSION 2
+#define VPF_ABI_VERSION 3
 
 /* 16-bit operand type of crops / ViT activations / weights (fp32 accumulation either way) */
 #define VPF_DTYPE_BF16 0
@@ -54,6 +54,9 @@ typedef struct {
   int32_t heads;     /* H, D / H must be 64 */
   int32_t max_crops; /* capacity: largest n_crops of one vpf_vit_forward call */
   int32_t dtype;     /* VPF_DTYPE_BF16 (default) or VPF_DTYPE_F16 */
+  int32_t crop_size; /* S: input crop size in pixels, 0 or 224 = the default; a smaller multiple
+                        of 16 gives P = (S/16)^2 patches and T = P + 1 tokens per crop (SURVEY.md
+                        section 8f-2 "native-resolution crops"; oracle/vit.py resamples pos_embed) */
 } vpf_vit_config;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -84,16 +87,16 @@ double vpf_resample_uniform(uint64_t seed, uint32_t frame_idx, uint32_t stream_i
 
 /* ---- a4: crop + bilinear resize + normalise + patchify (README.md:7; oracle/crop.py, D3/D4) -
  * frame: uint8 [H][W][3]; boxes come either from the SoA state (w = w0*exp(s), h = h0*exp(s))
- * or from an explicit [n][4] (cx,cy,w,h) array.  out: bf16 or fp16 (`dtype`) [n*196][768],
- * k = c*256+ky*16+kx.                                                                        */
+ * or from an explicit [n][4] (cx,cy,w,h) array.  crop_size S: 224, or a smaller multiple of 16.
+ * out: bf16 or fp16 (`dtype`) [n*(S/16)^2][768], k = c*256+ky*16+kx.                           */
 int vpf_crop_state(const uint8_t* frame, int H, int W, const float* state, int n, int ld,
-                   float w0, float h0, void* out16, int dtype, void* stream);
+                   float w0, float h0, void* out16, int dtype, int crop_size, void* stream);
 int vpf_crop_boxes(const uint8_t* frame, int H, int W, const float* boxes, int n,
-                   void* out16, int dtype, void* stream);
+                   void* out16, int dtype, int crop_size, void* stream);
 
 /* ---- a5: ViT/16 encoder (README.md:7; oracle/vit.py, D1/D2) --------------------------------
  * weights: array of VPF_VIT_N_GLOBAL + 12*depth + 2 device pointers in this order:
- *   patch_w bf16[D][768], patch_b f32[D], cls f32[D], pos f32[197][D],
+ *   patch_w bf16[D][768], patch_b f32[D], cls f32[D], pos f32[T][D] (T = 197 at crop size 224),
  *   per block: ln1_g, ln1_b f32[D]; qkv_w bf16[3D][D], qkv_b f32[3D]; proj_w bf16[D][D],
  *              proj_b f32[D]; ln2_g, ln2_b f32[D]; fc1_w bf16[4D][D], fc1_b f32[4D];
  *              fc2_w bf16[D][4D], fc2_b f32[D];
@@ -106,16 +109,19 @@ int vpf_vit_destroy(vpf_vit* h);
 size_t vpf_vit_workspace_bytes(const vpf_vit_config* cfg);
 int vpf_vit_set_weights(vpf_vit* h, const void* const* dev_ptrs, int n_ptrs);
 int vpf_vit_set_workspace(vpf_vit* h, void* workspace, size_t bytes);
-/* patches: bf16 [n_crops*196][768] (output of vpf_crop_*); emb: f32 [n_crops][D].             */
+/* patches: bf16 [n_crops*P][768] (output of vpf_crop_*, P = 196 at crop size 224);
+ * emb: f32 [n_crops][D].                                                                      */
 int vpf_vit_forward(vpf_vit* h, const void* patches_bf16, int n_crops, float* emb, void* stream);
 /* test hooks for single stages: C[M][N] = A[M][K] * W[N][K]^T (+ epilogue `mode`), LayerNorm,
  * attention.  mode: 0 bias->bf16, 1 bias+GELU->bf16, 2 bias+residual f32 in place,
- * 3 patch-embed (bias + pos, row remap into the 197-token stream, f32).                       */
+ * 3 patch-embed (bias + pos, row remap into the (patches_per_crop + 1)-token stream, f32).     */
 int vpf_gemm_bf16(const void* A, const void* W, const float* bias, void* out, const float* pos,
-                  int M, int N, int K, int mode, void* stream);
+                  int M, int N, int K, int mode, int patches_per_crop, void* stream);
 int vpf_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16,
                   int rows, int D, void* stream);
-int vpf_attention(const void* qkv_bf16, void* out_bf16, int n_crops, int heads, void* stream);
+/* qkv: bf16 [n_crops*tokens][3*64*heads], out: bf16 [n_crops*tokens][64*heads]; 2 <= tokens <= 197 */
+int vpf_attention(const void* qkv_bf16, void* out_bf16, int n_crops, int heads, int tokens,
+                  void* stream);
 /* number of kernels one vpf_vit_forward enqueues (for bench.py's gpu_launches claim).         */
 int vpf_vit_launches(const vpf_vit* h);
 

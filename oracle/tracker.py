@@ -28,7 +28,7 @@ class State(NamedTuple):
 class OracleTracker:
     def __init__(self, model="vit_base_patch16_224", n_particles=4096, seed=0, tau=0.1,
                  sigma_pos=None, sigma_vel=None, sigma_scale=0.01, sigma_init=None,
-                 state_dict=None, stream_id=0, vit_chunk=32):
+                 state_dict=None, stream_id=0, vit_chunk=32, crop_size=224):
         self.model = model
         self.n = int(n_particles)
         self.seed = int(seed)
@@ -37,12 +37,13 @@ class OracleTracker:
         self._sig = (sigma_pos, sigma_vel, sigma_scale, sigma_init)
         self.sd = state_dict if state_dict is not None else init_vit_weights(model)
         self.vit_chunk = vit_chunk
+        self.crop_size = int(crop_size)     # 224, or a smaller multiple of 16
         self.frame_idx = -1
         self.last = {}
 
     # -- helpers -----------------------------------------------------------------------------
     def embed(self, frame, boxes):
-        crops = crop_resize(np.asarray(frame), boxes)
+        crops = crop_resize(np.asarray(frame), boxes, size=self.crop_size)
         return vit_forward(crops, self.sd, self.model, chunk=self.vit_chunk)
 
     # -- API ---------------------------------------------------------------------------------

@@ -32,11 +32,32 @@ LN_EPS = 1e-6
 WEIGHT_SEED = 1234
 
 
-def vit_flops_per_crop(model: str) -> float:
-    """2*196*768*D + L*(24*197*D^2 + 4*197^2*D): full forward, 2 FLOP/MAC, no padding."""
+def vit_flops_per_crop(model: str, crop_size: int = 224) -> float:
+    """2*P*768*D + L*(24*T*D^2 + 4*T^2*D), P = (S/16)^2 patches, T = P + 1 tokens (196 / 197 at
+    S = 224): full forward, 2 FLOP/MAC, no padding."""
     c = VIT_CONFIGS[model]
     d, l = c["dim"], c["depth"]
-    return 2.0 * 196 * 768 * d + l * (24.0 * TOKENS * d * d + 4.0 * TOKENS * TOKENS * d)
+    p = (crop_size // 16) ** 2
+    t = p + 1
+    return 2.0 * p * 768 * d + l * (24.0 * t * d * d + 4.0 * t * t * d)
+
+
+def resample_pos_embed(pos_embed: torch.Tensor, grid: int) -> torch.Tensor:
+    """pos_embed [1, 1+14*14, D] -> [1, 1+grid*grid, D] for a (16*grid)^2 input.
+
+    Restates timm's ``resample_abs_pos_embed`` (what ``dynamic_img_size`` / a changed ``img_size``
+    applies to `vit_*_patch16_224` weights): the class-token row is kept, the 14x14 grid part is
+    resized with bicubic interpolation, antialias on, align_corners off, in fp32."""
+    n_tok, d = pos_embed.shape[1], pos_embed.shape[2]
+    old = int(round(math.sqrt(n_tok - 1)))
+    assert old * old + 1 == n_tok, "pos_embed must be [1, 1+g*g, D]"
+    if grid == old:
+        return pos_embed
+    cls_row, grid_rows = pos_embed[:, :1], pos_embed[:, 1:]
+    g = grid_rows.reshape(1, old, old, d).permute(0, 3, 1, 2).to(torch.float32)
+    g = F.interpolate(g, size=(grid, grid), mode="bicubic", antialias=True, align_corners=False)
+    g = g.permute(0, 2, 3, 1).reshape(1, grid * grid, d)
+    return torch.cat([cls_row.to(torch.float32), g], dim=1)
 
 
 def weight_keys(model: str):
@@ -85,18 +106,22 @@ def init_vit_weights(model: str, seed: int = WEIGHT_SEED) -> dict:
 
 @torch.no_grad()
 def vit_forward(crops, sd: dict, model: str, chunk: int = 32, return_tokens: bool = False):
-    """crops fp32 [N,3,224,224] (numpy or torch) -> CLS embedding fp32 [N,D] (numpy)."""
+    """crops fp32 [N,3,S,S] (numpy or torch; S = 224, or a smaller multiple of 16 with the
+    position embedding resampled to the (S/16)^2 grid) -> CLS embedding fp32 [N,D] (numpy)."""
     c = VIT_CONFIGS[model]
     d, depth, heads = c["dim"], c["depth"], c["heads"]
     hd = d // heads
     x_all = torch.as_tensor(np.asarray(crops), dtype=torch.float32)
+    grid = x_all.shape[-1] // 16
+    TOKENS = grid * grid + 1                                   # noqa: N806 (197 at S = 224)
+    pos_embed = resample_pos_embed(sd["pos_embed"], grid)
     outs = []
     for s in range(0, x_all.shape[0], chunk):
         x = x_all[s:s + chunk]
         n = x.shape[0]
         x = F.conv2d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=16)
-        x = x.flatten(2).transpose(1, 2)                       # [n,196,D], patch index = py*14+px
-        x = torch.cat([sd["cls_token"].expand(n, -1, -1), x], dim=1) + sd["pos_embed"]
+        x = x.flatten(2).transpose(1, 2)                       # [n,P,D], patch index = py*grid+px
+        x = torch.cat([sd["cls_token"].expand(n, -1, -1), x], dim=1) + pos_embed
         for i in range(depth):
             p = f"blocks.{i}."
             h = F.layer_norm(x, (d,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], LN_EPS)

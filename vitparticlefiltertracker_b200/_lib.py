@@ -13,10 +13,11 @@ _u64, _u32, _size_t = C.c_uint64, C.c_uint32, C.c_size_t
 
 class VitConfig(C.Structure):
     _fields_ = [("dim", C.c_int32), ("depth", C.c_int32), ("heads", C.c_int32),
-                ("max_crops", C.c_int32), ("dtype", C.c_int32)]
+                ("max_crops", C.c_int32), ("dtype", C.c_int32), ("crop_size", C.c_int32)]
 
 
 DTYPE_BF16, DTYPE_F16 = 0, 1
+ABI_VERSION = 3          # VPF_ABI_VERSION in include/vpf.h
 
 
 # name -> (restype, argtypes); mirrors include/vpf.h one to one
@@ -36,9 +37,9 @@ SIGNATURES = {
     "vpf_normals_fill": (_c_int, [_c_void_p, _c_int, _u32, _u32, _u32, _u64, _c_void_p]),
     "vpf_resample_uniform": (_c_double, [_u64, _u32, _u32]),
     "vpf_crop_state": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_int, _c_float,
-                                _c_float, _c_void_p, _c_int, _c_void_p]),
+                                _c_float, _c_void_p, _c_int, _c_int, _c_void_p]),
     "vpf_crop_boxes": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_int,
-                                _c_void_p]),
+                                _c_int, _c_void_p]),
     "vpf_vit_create": (_c_int, [C.POINTER(_c_void_p), C.POINTER(VitConfig)]),
     "vpf_vit_destroy": (_c_int, [_c_void_p]),
     "vpf_vit_workspace_bytes": (_size_t, [C.POINTER(VitConfig)]),
@@ -46,10 +47,10 @@ SIGNATURES = {
     "vpf_vit_set_workspace": (_c_int, [_c_void_p, _c_void_p, _size_t]),
     "vpf_vit_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p]),
     "vpf_gemm_bf16": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
-                               _c_int, _c_int, _c_int, _c_void_p]),
+                               _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "vpf_layernorm": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                                _c_void_p]),
-    "vpf_attention": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
+    "vpf_attention": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "vpf_vit_launches": (_c_int, [_c_void_p]),
     "vpf_loglik": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_float, _c_void_p, _c_void_p,
                             _c_void_p]),
@@ -82,7 +83,7 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)      # AttributeError here == ABI mismatch with include/vpf.h
         fn.restype = res
         fn.argtypes = args
-    if lib.vpf_abi_version() != 2:
+    if lib.vpf_abi_version() != ABI_VERSION:
         raise RuntimeError("libvpf.so ABI version mismatch")
     _lib = lib
     return lib

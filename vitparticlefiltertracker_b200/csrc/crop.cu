@@ -2,10 +2,11 @@
 // Oracle: oracle/crop.py crop_resize + patchify (upstream anchor
 // README.md:7, the input side of ViT feature extraction).
 //
-// HBM-write bound by construction: 3*224*224 bf16 = 301 056 B written per particle; the uint8
-// frame (<= 6.2 MB) lives in L2.  One CTA produces two patch rows (32 x 224 output pixels) of
-// one crop:
-//   1. the particle box and the 224 horizontal taps (x0, frac) -- identical for every output
+// HBM-write bound by construction: 3*S*S bf16 written per particle (301 056 B at the default crop
+// size S = 224; S is a run-time multiple of 16, see SURVEY.md section 8f-2 "native-resolution
+// crops"); the uint8 frame (<= 6.2 MB) lives in L2.  One CTA produces two patch rows (32 x S
+// output pixels) of one crop:
+//   1. the particle box and the S horizontal taps (x0, frac) -- identical for every output
 //      row of the crop -- are staged in shared memory once per CTA;
 //   2. the source rows the CTA touches are copied to shared memory with coalesced 4-byte loads
 //      (falls back to direct global taps when the box is too large to stage);
@@ -17,14 +18,10 @@
 
 namespace vpf {
 
-static constexpr int kCrop = 224;
+static constexpr int kMaxCrop = 224;
 static constexpr int kPatch = 16;
-static constexpr int kGridP = 14;
-static constexpr int kPatches = 196;
 static constexpr int kPatchK = 768;
-static constexpr int kSplit = 7;                          // CTAs per crop
-static constexpr int kPatchesPerCta = kPatches / kSplit;  // 28 = two patch rows
-static constexpr int kRowsPerCta = 2 * kPatch;            // 32 output rows
+static constexpr int kRowsPerCta = 2 * kPatch;            // 32 output rows = two patch rows
 static constexpr int kStageWords = 9 * 1024;              // 36 KB of staged source rows
 
 struct Box {
@@ -40,10 +37,13 @@ template <bool kFromState>
 __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ frame, int H, int W,
                                                     const float* __restrict__ src, int n, int ld,
                                                     float w0, float h0,
-                                                    __nv_bfloat16* __restrict__ out, bool f16) {
+                                                    __nv_bfloat16* __restrict__ out, bool f16,
+                                                    int S /* output crop size, multiple of 16 */) {
   __shared__ uint32_t stage[kStageWords];
-  __shared__ float s_fx[kCrop];
-  __shared__ int s_x0[kCrop];
+  __shared__ float s_fx[kMaxCrop];
+  __shared__ int s_x0[kMaxCrop];
+  const int grid_p = S / kPatch;                         // patches per row / column
+  const int crop_patches = grid_p * grid_p;
   const int crop = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Box b;
@@ -57,15 +57,18 @@ __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ f
     b.cx = src[crop * 4 + 0]; b.cy = src[crop * 4 + 1];
     b.w = src[crop * 4 + 2];  b.h = src[crop * 4 + 3];
   }
-  const float stepx = __fdiv_rn(b.w, (float)kCrop), stepy = __fdiv_rn(b.h, (float)kCrop);
+  const float stepx = __fdiv_rn(b.w, (float)S), stepy = __fdiv_rn(b.h, (float)S);
   const float basex = __fsub_rn(__fsub_rn(b.cx, __fmul_rn(0.5f, b.w)), 0.5f);
   const float basey = __fsub_rn(__fsub_rn(b.cy, __fmul_rn(0.5f, b.h)), 0.5f);
   const float xmax = (float)(W - 1), ymax = (float)(H - 1);
   const float c255 = 2.0f / 255.0f;
   const int i0 = blockIdx.y * kRowsPerCta;
+  const int n_rows = min(kRowsPerCta, S - i0);           // 32, or 16 for an odd last patch row
+  const int first_patch = 2 * blockIdx.y * grid_p;
+  const int n_patches = (n_rows / kPatch) * grid_p;
 
   // ---- horizontal taps, shared by every output row ----
-  if (threadIdx.x < kCrop) {
+  if (threadIdx.x < S) {
     const float xs = sample_coord(basex, stepx, threadIdx.x, xmax);
     const float x0f = floorf(xs);
     s_fx[threadIdx.x] = __fsub_rn(xs, x0f);
@@ -73,9 +76,9 @@ __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ f
   }
   // ---- source window of this CTA (coordinates are monotone in the output index) ----
   const int y_lo = (int)floorf(sample_coord(basey, stepy, i0, ymax));
-  const int y_hi = min((int)floorf(sample_coord(basey, stepy, i0 + kRowsPerCta - 1, ymax)) + 1, H - 1);
+  const int y_hi = min((int)floorf(sample_coord(basey, stepy, i0 + n_rows - 1, ymax)) + 1, H - 1);
   const int x_lo = (int)floorf(sample_coord(basex, stepx, 0, xmax));
-  const int x_hi = min((int)floorf(sample_coord(basex, stepx, kCrop - 1, xmax)) + 1, W - 1);
+  const int x_hi = min((int)floorf(sample_coord(basex, stepx, S - 1, xmax)) + 1, W - 1);
   const int rows = y_hi - y_lo + 1;
   const int row_bytes = (x_hi - x_lo + 1) * 3;
   const int pitch = (row_bytes + 6) / 4 + 1;                  // words per staged row
@@ -100,9 +103,9 @@ __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ f
   const uint8_t* sbytes = reinterpret_cast<const uint8_t*>(stage);
   const int ky = lane >> 1, kx0 = (lane & 1) * 8;
 
-  for (int pl = warp; pl < kPatchesPerCta; pl += 8) {
-    const int p = blockIdx.y * kPatchesPerCta + pl;
-    const int py = p / kGridP, px = p - py * kGridP;
+  for (int pl = warp; pl < n_patches; pl += 8) {
+    const int p = first_patch + pl;
+    const int py = p / grid_p, px = p - py * grid_p;
     const int i = py * kPatch + ky;
     const float ys = sample_coord(basey, stepy, i, ymax);
     const float y0f = floorf(ys);
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ f
         v[c][e] = pack16(__fsub_rn(__fmul_rn(val, c255), 1.0f), f16);
       }
     }
-    __nv_bfloat16* dst = out + ((size_t)crop * kPatches + p) * kPatchK + ky * kPatch + kx0;
+    __nv_bfloat16* dst = out + ((size_t)crop * crop_patches + p) * kPatchK + ky * kPatch + kx0;
 #pragma unroll
     for (int c = 0; c < 3; ++c)
       *reinterpret_cast<uint4*>(dst + c * 256) = *reinterpret_cast<const uint4*>(v[c]);
@@ -151,26 +154,34 @@ using namespace vpf;
 
 extern "C" {
 
+static bool crop_size_ok(int s) { return s >= kPatch && s <= kMaxCrop && s % kPatch == 0; }
+
 int vpf_crop_state(const uint8_t* frame, int H, int W, const float* state, int n, int ld,
-                   float w0, float h0, void* out_bf16, int dtype, void* stream) {
+                   float w0, float h0, void* out_bf16, int dtype, int crop_size, void* stream) {
   VPF_REQUIRE(dtype == VPF_DTYPE_BF16 || dtype == VPF_DTYPE_F16, "vpf_crop_state: bad dtype");
+  VPF_REQUIRE(crop_size_ok(crop_size), "vpf_crop_state: crop_size %d must be a multiple of 16 in [16, 224]", crop_size);
   VPF_REQUIRE(frame && state && out_bf16 && H > 0 && W > 0 && n > 0 && ld >= n,
               "vpf_crop_state: bad arguments");
   VPF_REQUIRE(((uintptr_t)out_bf16 & 15) == 0, "vpf_crop_state: out must be 16-byte aligned");
-  crop_kernel<true><<<dim3(n, kSplit), 256, 0, (cudaStream_t)stream>>>(
-      frame, H, W, state, n, ld, w0, h0, (__nv_bfloat16*)out_bf16, dtype == VPF_DTYPE_F16);
+  crop_kernel<true><<<dim3(n, (crop_size + kRowsPerCta - 1) / kRowsPerCta), 256, 0,
+                      (cudaStream_t)stream>>>(frame, H, W, state, n, ld, w0, h0,
+                                              (__nv_bfloat16*)out_bf16, dtype == VPF_DTYPE_F16,
+                                              crop_size);
   VPF_LAUNCH_CHECK();
   return VPF_OK;
 }
 
 int vpf_crop_boxes(const uint8_t* frame, int H, int W, const float* boxes, int n, void* out_bf16,
-                   int dtype, void* stream) {
+                   int dtype, int crop_size, void* stream) {
   VPF_REQUIRE(dtype == VPF_DTYPE_BF16 || dtype == VPF_DTYPE_F16, "vpf_crop_boxes: bad dtype");
+  VPF_REQUIRE(crop_size_ok(crop_size), "vpf_crop_boxes: crop_size %d must be a multiple of 16 in [16, 224]", crop_size);
   VPF_REQUIRE(frame && boxes && out_bf16 && H > 0 && W > 0 && n > 0,
               "vpf_crop_boxes: bad arguments");
   VPF_REQUIRE(((uintptr_t)out_bf16 & 15) == 0, "vpf_crop_boxes: out must be 16-byte aligned");
-  crop_kernel<false><<<dim3(n, kSplit), 256, 0, (cudaStream_t)stream>>>(
-      frame, H, W, boxes, n, 0, 1.f, 1.f, (__nv_bfloat16*)out_bf16, dtype == VPF_DTYPE_F16);
+  crop_kernel<false><<<dim3(n, (crop_size + kRowsPerCta - 1) / kRowsPerCta), 256, 0,
+                       (cudaStream_t)stream>>>(frame, H, W, boxes, n, 0, 1.f, 1.f,
+                                               (__nv_bfloat16*)out_bf16, dtype == VPF_DTYPE_F16,
+                                               crop_size);
   VPF_LAUNCH_CHECK();
   return VPF_OK;
 }

@@ -25,7 +25,7 @@ enum GemmMode : int {
   kBiasBf16 = 0,      // out bf16 [M][N] = acc + bias
   kBiasGeluBf16 = 1,  // out bf16 [M][N] = gelu(acc + bias)           (exact-erf GELU)
   kBiasResidualF32 = 2,  // X f32 [M][N] += acc + bias                (in place)
-  kPatchEmbedF32 = 3,  // X f32 [(r/196)*197 + 1 + r%196][N] = acc + bias + pos[1 + r%196][N]
+  kPatchEmbedF32 = 3,  // X f32 [(r/P)*(P+1) + 1 + r%P][N] = acc + bias + pos[1 + r%P][N], P = ppc
   // internal variant of mode 2, chosen by the launcher for small K (HBM-bound GEMMs such as proj):
   // the fp32 residual tile is loaded, updated in place and stored entirely by the TMA unit
   kBiasResidualF32Tma = 4
@@ -37,6 +37,7 @@ struct GemmArgs {
   void* out;
   const float* pos;
   int f16 = 0;   // 16-bit operand / output type: 0 = bf16, 1 = fp16
+  int ppc = 196; // patch-embed mode: patches per crop (196 at crop size 224); tokens = ppc + 1
 };
 
 static constexpr int kBlockM = 128;
@@ -195,8 +196,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
       dst[i] = nullptr;
       if (grow < g.M) {
         if (MODE == kPatchEmbedF32) {
-          const int crop = grow / 196, pp = grow - crop * 196;
-          dst[i] = reinterpret_cast<float4*>(X + ((size_t)crop * 197 + 1 + pp) * g.N + col) + p;
+          const int crop = grow / g.ppc, pp = grow - crop * g.ppc;
+          dst[i] = reinterpret_cast<float4*>(X + ((size_t)crop * (g.ppc + 1) + 1 + pp) * g.N + col) + p;
           res[i] = __ldg(reinterpret_cast<const float4*>(g.pos + (size_t)(1 + pp) * g.N + col) + p);
         } else {
           dst[i] = reinterpret_cast<float4*>(X + (size_t)grow * g.N + col) + p;

@@ -99,13 +99,13 @@ static int pick_block_n(int N) {
   return 0;
 }
 
-// 3-D view [crop][token][3D] of the fused qkv buffer: the TMA unit zero-fills tokens >= 197.
+// 3-D view [crop][token][3D] of the fused qkv buffer: the TMA unit zero-fills tokens >= T.
 static int make_qkv_map(CUtensorMap* map, const void* ptr, int n_crops, int D, uint32_t box_tokens,
-                        int ncols3 = 3) {
+                        int T, int ncols3 = 3) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return VPF_ERR_CUDA; }
-  cuuint64_t dims[3] = {(cuuint64_t)ncols3 * D, (cuuint64_t)kTokens, (cuuint64_t)n_crops};
-  cuuint64_t strides[2] = {(cuuint64_t)ncols3 * D * 2, (cuuint64_t)kTokens * ncols3 * D * 2};
+  cuuint64_t dims[3] = {(cuuint64_t)ncols3 * D, (cuuint64_t)T, (cuuint64_t)n_crops};
+  cuuint64_t strides[2] = {(cuuint64_t)ncols3 * D * 2, (cuuint64_t)T * ncols3 * D * 2};
   cuuint32_t box[3] = {64, box_tokens, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides,
@@ -275,11 +275,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 // X[crop*197][:] = cls + pos[0]
 __global__ void cls_init_kernel(float* __restrict__ X, const float* __restrict__ cls,
-                                const float* __restrict__ pos, int n_crops, int D) {
+                                const float* __restrict__ pos, int n_crops, int D, int T) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_crops * D) return;
   int crop = i / D, d = i - crop * D;
-  X[(size_t)crop * kTokens * D + d] = cls[d] + pos[d];
+  X[(size_t)crop * T * D + d] = cls[d] + pos[d];
 }
 
 // VPF_ATTN=mma selects the warp-level mma.sync kernel; default is the tcgen05 kernel.
@@ -292,11 +292,29 @@ static bool attn_use_tc() {
   return v == 1;
 }
 
+template <int KT>
+static int launch_attention_small(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_crops,
+                                  int heads, int tokens, cudaStream_t s, int f16) {
+  static bool attr[32] = {};
+  if (first_time_on_device(attr))
+    VPF_CUDA(cudaFuncSetAttribute(attention_small_kernel<KT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SmallAttn<KT>::kSmem));
+  const int n_pairs = n_crops * heads;
+  attention_small_kernel<KT><<<(n_pairs + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32,
+                               SmallAttn<KT>::kSmem, s>>>(qkv, out, n_pairs, heads, tokens, f16 != 0);
+  VPF_LAUNCH_CHECK();
+  return VPF_OK;
+}
+
+// T = 197 (224-pixel crops): tcgen05 kernel.  Smaller crop sizes: one warp per (crop, head) for
+// T <= 64, the CTA-per-pair mma.sync kernel above that.
 static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_crops, int heads,
-                            const CUtensorMap* mq, const CUtensorMap* mkv, cudaStream_t s,
-                            int f16 = 0) {
+                            int tokens, const CUtensorMap* mq, const CUtensorMap* mkv,
+                            cudaStream_t s, int f16 = 0) {
   const int D = heads * kHeadDim;
-  if (attn_use_tc()) {
+  if (tokens <= 32) return launch_attention_small<32>(qkv, out, n_crops, heads, tokens, s, f16);
+  if (tokens <= 64) return launch_attention_small<64>(qkv, out, n_crops, heads, tokens, s, f16);
+  if (tokens == attn::kT && attn_use_tc()) {
     static bool attr[32] = {};
     if (first_time_on_device(attr))
       VPF_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel,
@@ -306,12 +324,12 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_
     attn::attention_tc_kernel<<<grid, attn::kThreads, attn::kSmemBytes, s>>>(*mq, *mkv, out, n_pairs,
                                                                              heads, D, f16);
   } else {
-    if (f16) { set_error("VPF_ATTN=mma supports bf16 operands only"); return VPF_ERR_UNSUPPORTED; }
     static bool attr[32] = {};
     if (first_time_on_device(attr))
       VPF_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kAttnSmem));
-    attention_kernel<<<dim3(heads, n_crops), kAttnThreads, kAttnSmem, s>>>(qkv, out, D);
+    attention_kernel<<<dim3(heads, n_crops), kAttnThreads, kAttnSmem, s>>>(qkv, out, D, tokens,
+                                                                          f16 != 0);
   }
   VPF_LAUNCH_CHECK();
   return VPF_OK;
@@ -321,21 +339,22 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_
 // token's output depends on the other tokens only through their keys and values) --------------
 // Xc[crop][:] = X[crop*197][:]
 __global__ void gather_cls_kernel(const float* __restrict__ X, float* __restrict__ Xc, int n_crops,
-                                  int D) {
+                                  int D, int T) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;     // float4 index
   const int nv = D >> 2;
   if (i >= n_crops * nv) return;
   int crop = i / nv, v = i - crop * nv;
   reinterpret_cast<float4*>(Xc)[i] =
-      reinterpret_cast<const float4*>(X + (size_t)crop * kTokens * D)[v];
+      reinterpret_cast<const float4*>(X + (size_t)crop * T * D)[v];
 }
 
 // One warp per (crop, head): o = softmax(q K^T / 8) V for the single CLS query.
-// q: bf16 [n_crops][D]; kv: bf16 [n_crops*197][2D] (K then V); o: bf16 [n_crops][D].
+// q: bf16 [n_crops][D]; kv: bf16 [n_crops*T][2D] (K then V); o: bf16 [n_crops][D].  T <= 224.
 __global__ void __launch_bounds__(256) cls_attention_kernel(const __nv_bfloat16* __restrict__ q,
                                                             const __nv_bfloat16* __restrict__ kv,
                                                             __nv_bfloat16* __restrict__ o,
-                                                            int n_pairs, int heads, bool f16) {
+                                                            int n_pairs, int heads, bool f16,
+                                                            int T) {
   const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (pair >= n_pairs) return;
@@ -355,7 +374,7 @@ __global__ void __launch_bounds__(256) cls_attention_kernel(const __nv_bfloat16*
       }
     }
   }
-  const __nv_bfloat16* kbase = kv + (size_t)crop * kTokens * 2 * D + head * kHeadDim;
+  const __nv_bfloat16* kbase = kv + (size_t)crop * T * 2 * D + head * kHeadDim;
   const float c = 0.125f * 1.4426950408889634f;
   float sc[7];
   float m = -INFINITY;
@@ -363,7 +382,7 @@ __global__ void __launch_bounds__(256) cls_attention_kernel(const __nv_bfloat16*
   for (int i = 0; i < 7; ++i) {
     const int j = i * 32 + lane;
     float acc = -INFINITY;
-    if (j < kTokens) {
+    if (j < T) {
       const uint4* k4 = reinterpret_cast<const uint4*>(kbase + (size_t)j * 2 * D);
       acc = 0.f;
 #pragma unroll
@@ -398,7 +417,7 @@ __global__ void __launch_bounds__(256) cls_attention_kernel(const __nv_bfloat16*
     for (int jj = 0; jj < 32; ++jj) {
       const int j = i * 32 + jj;
       const float p = __shfl_sync(0xffffffffu, sc[i], jj);
-      if (j < kTokens) {
+      if (j < T) {
         float2 f = unpack16x2(*reinterpret_cast<const uint32_t*>(vbase + (size_t)j * 2 * D), f16);
         o0 = fmaf(p, f.x, o0);
         o1 = fmaf(p, f.y, o1);
@@ -422,6 +441,8 @@ using namespace vpf;
 
 struct vpf_vit {
   vpf_vit_config cfg;
+  int tokens = kMaxTokens;      // T = ppc + 1
+  int ppc = kMaxTokens - 1;     // patches per crop = (crop_size / 16)^2
   bool has_weights = false, has_ws = false;
   const void* patch_w = nullptr;
   const float *patch_b = nullptr, *cls = nullptr, *pos = nullptr, *norm_g = nullptr,
@@ -432,6 +453,7 @@ struct vpf_vit {
   float* X = nullptr;           // [max_rows][D] fp32 residual stream
   __nv_bfloat16* Xn = nullptr;  // [max_rows][D] LN output / attention output
   __nv_bfloat16* big = nullptr; // [max_rows][4D] qkv ([..][3D]) or fc1 output
+  uint8_t* cbuf = nullptr;      // compact operands of the CLS-only last block (cls_bytes)
   // activation tensor maps, cached for the last n_crops
   int maps_for = -1;
   const void* maps_patches = nullptr;
@@ -442,6 +464,19 @@ struct vpf_vit {
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// compact [n][..] operands of the CLS-only last block: q, o, xn (16-bit [n][D]), hc (16-bit
+// [n][4D]), xc (f32 [n][D]), each 256-byte aligned
+static size_t cls_bytes(size_t n, size_t D) {
+  return 3 * align_up(n * D * 2, 256) + align_up(n * 4 * D * 2, 256) + align_up(n * D * 4, 256);
+}
+
+// crop_size 0 means the default 224; otherwise a multiple of 16 in [16, 224]
+static int tokens_of(const vpf_vit_config* cfg) {
+  const int s = cfg->crop_size ? cfg->crop_size : 224;
+  if (s < 16 || s > 224 || s % 16) return 0;
+  return (s / 16) * (s / 16) + 1;
+}
 
 extern "C" {
 
@@ -455,12 +490,16 @@ int vpf_vit_create(vpf_vit** out, const vpf_vit_config* cfg) {
               "vpf_vit_create: need dim = 64*heads <= 1024, depth > 0, max_crops > 0");
   VPF_REQUIRE(cfg->dtype == VPF_DTYPE_BF16 || cfg->dtype == VPF_DTYPE_F16,
               "vpf_vit_create: dtype must be VPF_DTYPE_BF16 or VPF_DTYPE_F16");
+  VPF_REQUIRE(tokens_of(cfg) > 0, "vpf_vit_create: crop_size %d must be 0 (= 224) or a multiple of 16 in [16, 224]",
+              cfg->crop_size);
   if (!pick_block_n(cfg->dim) || !pick_block_n(3 * cfg->dim)) {
     set_error("vpf_vit_create: dim %d unsupported (dim and 3*dim must be multiples of 128)", cfg->dim);
     return VPF_ERR_UNSUPPORTED;
   }
   vpf_vit* h = new vpf_vit();
   h->cfg = *cfg;
+  h->tokens = tokens_of(cfg);
+  h->ppc = h->tokens - 1;
   h->layers.resize(cfg->depth);
   {
     const char* e = getenv("VPF_CLS_PRUNE");    // VPF_CLS_PRUNE=0: run the last block on all rows
@@ -476,10 +515,10 @@ int vpf_vit_destroy(vpf_vit* h) {
 }
 
 size_t vpf_vit_workspace_bytes(const vpf_vit_config* cfg) {
-  if (!cfg) return 0;
-  const size_t rows = (size_t)cfg->max_crops * kTokens, D = cfg->dim;
+  if (!cfg || !tokens_of(cfg)) return 0;
+  const size_t rows = (size_t)cfg->max_crops * tokens_of(cfg), D = cfg->dim;
   return align_up(rows * D * 4, 1024) + align_up(rows * D * 2, 1024) +
-         align_up(rows * 4 * D * 2, 1024) + 1024;
+         align_up(rows * 4 * D * 2, 1024) + cls_bytes(cfg->max_crops, D) + 1024;
 }
 
 int vpf_vit_set_weights(vpf_vit* h, const void* const* p, int n) {
@@ -523,11 +562,12 @@ int vpf_vit_set_workspace(vpf_vit* h, void* ws, size_t bytes) {
   VPF_REQUIRE(((uintptr_t)ws & 1023) == 0, "vpf_vit_set_workspace: workspace must be 1024-byte aligned");
   VPF_REQUIRE(bytes >= vpf_vit_workspace_bytes(&h->cfg),
               "vpf_vit_set_workspace: need %zu bytes, got %zu", vpf_vit_workspace_bytes(&h->cfg), bytes);
-  const size_t rows = (size_t)h->cfg.max_crops * kTokens, D = h->cfg.dim;
+  const size_t rows = (size_t)h->cfg.max_crops * h->tokens, D = h->cfg.dim;
   uint8_t* b = (uint8_t*)ws;
   h->X = (float*)b;            b += align_up(rows * D * 4, 1024);
   h->Xn = (__nv_bfloat16*)b;   b += align_up(rows * D * 2, 1024);
-  h->big = (__nv_bfloat16*)b;
+  h->big = (__nv_bfloat16*)b;  b += align_up(rows * 4 * D * 2, 1024);
+  h->cbuf = b;
   h->has_ws = true;
   h->maps_for = -1;
   return VPF_OK;
@@ -542,7 +582,7 @@ int vpf_vit_launches(const vpf_vit* h) {
 
 // One full encoder block on every token row.
 static int run_block(vpf_vit* h, const LayerW& w, int n, cudaStream_t s) {
-  const int D = h->cfg.dim, H = h->cfg.heads, M = n * kTokens;
+  const int D = h->cfg.dim, H = h->cfg.heads, M = n * h->tokens;
   const int f16 = h->cfg.dtype == VPF_DTYPE_F16;
   const int ln_blocks = (M + 7) / 8;
   int rc;
@@ -553,7 +593,7 @@ static int run_block(vpf_vit* h, const LayerW& w, int n, cudaStream_t s) {
       g.f16 = f16;
     if ((rc = launch_gemm(h->a_xn, w.m_qkv, g, kBiasBf16, s))) return rc;
   }
-  if ((rc = launch_attention(h->big, h->Xn, n, H, &h->a_q, &h->a_kv, s, f16))) return rc;
+  if ((rc = launch_attention(h->big, h->Xn, n, H, h->tokens, &h->a_q, &h->a_kv, s, f16))) return rc;
   {
     GemmArgs g{M, D, D, w.proj_b, h->X, nullptr};
       g.f16 = f16;
@@ -575,14 +615,14 @@ static int run_block(vpf_vit* h, const LayerW& w, int n, cudaStream_t s) {
 }
 
 // Last block, CLS rows only (exact): keys / values for every token, everything else for the n
-// CLS rows.  Compact operands live in the unused upper part of `big`.
+// CLS rows.  Compact operands live in their own workspace region (`cbuf`).
 struct ClsBufs {
   __nv_bfloat16 *q, *o, *xn, *hc;
   float* xc;
 };
 static ClsBufs cls_bufs(const vpf_vit* h, int n) {
-  const size_t D = h->cfg.dim, M = (size_t)n * kTokens;
-  uint8_t* b = reinterpret_cast<uint8_t*>(h->big) + align_up(M * 2 * D * 2, 256);
+  const size_t D = h->cfg.dim;
+  uint8_t* b = h->cbuf;
   ClsBufs c;
   c.q = (__nv_bfloat16*)b;  b += align_up((size_t)n * D * 2, 256);
   c.o = (__nv_bfloat16*)b;  b += align_up((size_t)n * D * 2, 256);
@@ -593,7 +633,7 @@ static ClsBufs cls_bufs(const vpf_vit* h, int n) {
 }
 
 static int run_last_block_cls(vpf_vit* h, const LayerW& w, int n, float* emb, cudaStream_t s) {
-  const int D = h->cfg.dim, H = h->cfg.heads, M = n * kTokens;
+  const int D = h->cfg.dim, H = h->cfg.heads, T = h->tokens, M = n * T;
   const int f16 = h->cfg.dtype == VPF_DTYPE_F16;
   const ClsBufs c = cls_bufs(h, n);
   int rc;
@@ -609,9 +649,9 @@ static int run_last_block_cls(vpf_vit* h, const LayerW& w, int n, float* emb, cu
       g.f16 = f16;
     if ((rc = launch_gemm(h->a_xn_cls, h->m_q_last, g, kBiasBf16, s))) return rc;
   }
-  cls_attention_kernel<<<(n * H + 7) / 8, 256, 0, s>>>(c.q, h->big, c.o, n * H, H, f16 != 0);
+  cls_attention_kernel<<<(n * H + 7) / 8, 256, 0, s>>>(c.q, h->big, c.o, n * H, H, f16 != 0, T);
   VPF_LAUNCH_CHECK();
-  gather_cls_kernel<<<(n * (D / 4) + 255) / 256, 256, 0, s>>>(h->X, c.xc, n, D);
+  gather_cls_kernel<<<(n * (D / 4) + 255) / 256, 256, 0, s>>>(h->X, c.xc, n, D, T);
   VPF_LAUNCH_CHECK();
   {
     GemmArgs g{n, D, D, w.proj_b, c.xc, nullptr};
@@ -644,17 +684,19 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
   VPF_REQUIRE(n > 0 && n <= h->cfg.max_crops, "vpf_vit_forward: n_crops %d outside [1, %d]", n,
               h->cfg.max_crops);
   cudaStream_t s = (cudaStream_t)stream;
-  const int D = h->cfg.dim, L = h->cfg.depth;
-  const int M0 = n * 196, M = n * kTokens;
+  const int D = h->cfg.dim, L = h->cfg.depth, T = h->tokens;
+  const int M0 = n * h->ppc, M = n * T;
   int rc;
   if (h->maps_for != n || h->maps_patches != patches) {
     if ((rc = make_map(&h->a_patches, patches, M0, 768, kBlockM))) return rc;
     if ((rc = make_map(&h->a_xn, h->Xn, M, D, kBlockM))) return rc;
     if ((rc = make_map(&h->a_big, h->big, M, 4 * D, kBlockM))) return rc;
-    if ((rc = make_qkv_map(&h->a_q, h->big, n, D, 128))) return rc;
-    if ((rc = make_qkv_map(&h->a_kv, h->big, n, D, attn::kKeys))) return rc;
+    if (T == attn::kT) {      // tcgen05 attention (smaller crop sizes use the mma.sync kernels)
+      if ((rc = make_qkv_map(&h->a_q, h->big, n, D, 128, T))) return rc;
+      if ((rc = make_qkv_map(&h->a_kv, h->big, n, D, attn::kKeys, T))) return rc;
+    }
     const ClsBufs c = cls_bufs(h, n);
-    if ((rc = make_map(&h->a_xn_cls, h->Xn, n, D, kBlockM, (uint64_t)kTokens * D))) return rc;
+    if ((rc = make_map(&h->a_xn_cls, h->Xn, n, D, kBlockM, (uint64_t)T * D))) return rc;
     if ((rc = make_map(&h->a_ocls, c.o, n, D, kBlockM))) return rc;
     if ((rc = make_map(&h->a_xnc, c.xn, n, D, kBlockM))) return rc;
     if ((rc = make_map(&h->a_hc, c.hc, n, 4 * D, kBlockM))) return rc;
@@ -662,18 +704,19 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
     h->maps_patches = patches;
   }
 
-  cls_init_kernel<<<(n * D + 255) / 256, 256, 0, s>>>(h->X, h->cls, h->pos, n, D);
+  cls_init_kernel<<<(n * D + 255) / 256, 256, 0, s>>>(h->X, h->cls, h->pos, n, D, T);
   VPF_LAUNCH_CHECK();
   {
     GemmArgs g{M0, D, 768, h->patch_b, h->X, h->pos};
     g.f16 = h->cfg.dtype == VPF_DTYPE_F16;
+    g.ppc = h->ppc;
     if ((rc = launch_gemm(h->a_patches, h->m_patch, g, kPatchEmbedF32, s))) return rc;
   }
   const int full_blocks = h->cls_prune ? L - 1 : L;
   for (int l = 0; l < full_blocks; ++l)
     if ((rc = run_block(h, h->layers[l], n, s))) return rc;
   if (h->cls_prune) return run_last_block_cls(h, h->layers[L - 1], n, emb, s);
-  layernorm_kernel<float><<<(n + 7) / 8, 256, 0, s>>>(h->X, (size_t)kTokens * D, h->norm_g,
+  layernorm_kernel<float><<<(n + 7) / 8, 256, 0, s>>>(h->X, (size_t)T * D, h->norm_g,
                                                      h->norm_b, emb, n, D);
   VPF_LAUNCH_CHECK();
   return VPF_OK;
@@ -681,10 +724,11 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
 
 // ---- single-stage test hooks ----------------------------------------------------------------
 int vpf_gemm_bf16(const void* A, const void* W, const float* bias, void* out, const float* pos,
-                  int M, int N, int K, int mode, void* stream) {
+                  int M, int N, int K, int mode, int patches_per_crop, void* stream) {
   VPF_REQUIRE(A && W && bias && out && M > 0 && N > 0 && K > 0, "vpf_gemm_bf16: bad arguments");
   VPF_REQUIRE(K % kBlockK == 0, "vpf_gemm_bf16: K=%d must be a multiple of 64", K);
-  VPF_REQUIRE(mode != kPatchEmbedF32 || pos, "vpf_gemm_bf16: patch-embed mode needs pos");
+  VPF_REQUIRE(mode != kPatchEmbedF32 || (pos && patches_per_crop > 0),
+              "vpf_gemm_bf16: patch-embed mode needs pos and patches_per_crop > 0");
   const int bn = pick_block_n(N);
   if (!bn) { set_error("vpf_gemm_bf16: N=%d must be a multiple of 128", N); return VPF_ERR_UNSUPPORTED; }
   CUtensorMap ma, mb;
@@ -692,6 +736,7 @@ int vpf_gemm_bf16(const void* A, const void* W, const float* bias, void* out, co
   if ((rc = make_map(&ma, A, M, K, kBlockM))) return rc;
   if ((rc = make_map(&mb, W, N, K, bn / gemm_ctas()))) return rc;
   GemmArgs g{M, N, K, bias, out, pos};
+  if (mode == kPatchEmbedF32) g.ppc = patches_per_crop;
   return launch_gemm(ma, mb, g, mode, (cudaStream_t)stream);
 }
 
@@ -705,14 +750,17 @@ int vpf_layernorm(const float* x, const float* gamma, const float* beta, void* o
   return VPF_OK;
 }
 
-int vpf_attention(const void* qkv, void* out, int n_crops, int heads, void* stream) {
-  VPF_REQUIRE(qkv && out && n_crops > 0 && heads > 0, "vpf_attention: bad arguments");
+int vpf_attention(const void* qkv, void* out, int n_crops, int heads, int tokens, void* stream) {
+  VPF_REQUIRE(qkv && out && n_crops > 0 && heads > 0 && tokens >= 2 && tokens <= kMaxTokens,
+              "vpf_attention: bad arguments (2 <= tokens <= 197)");
   CUtensorMap mq, mkv;
   int rc;
-  if ((rc = make_qkv_map(&mq, qkv, n_crops, heads * kHeadDim, 128))) return rc;
-  if ((rc = make_qkv_map(&mkv, qkv, n_crops, heads * kHeadDim, attn::kKeys))) return rc;
-  return launch_attention((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n_crops, heads, &mq, &mkv,
-                          (cudaStream_t)stream);
+  if (tokens == attn::kT) {
+    if ((rc = make_qkv_map(&mq, qkv, n_crops, heads * kHeadDim, 128, tokens))) return rc;
+    if ((rc = make_qkv_map(&mkv, qkv, n_crops, heads * kHeadDim, attn::kKeys, tokens))) return rc;
+  }
+  return launch_attention((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n_crops, heads, tokens,
+                          &mq, &mkv, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -20,24 +20,28 @@ from .vit_weights import VIT_CONFIGS, init_state_dict, pack_for_device
 
 class MultiStreamTracker:
     def __init__(self, n_streams, model="vit_base_patch16_224", n_particles=2048, seed=0,
-                 device="cuda", tau=0.1, sigma_scale=0.01, state_dict=None, first_stream_id=0):
+                 device="cuda", tau=0.1, sigma_scale=0.01, state_dict=None, first_stream_id=0,
+                 crop_size=224):
         if not torch.cuda.is_available():
             raise RuntimeError("MultiStreamTracker needs a CUDA device: there is no CPU fallback")
         self.S, self.n, self.seed, self.tau = int(n_streams), int(n_particles), int(seed), float(tau)
         self.model, self.device = model, torch.device(device)
+        self.crop_size = int(crop_size)
+        self.n_patch = ops.n_patch(self.crop_size)
         self.sigma_scale = float(np.float32(sigma_scale))
         self.stream_ids = [first_stream_id + s for s in range(self.S)]
         cfg = VIT_CONFIGS[model]
         self.dim = cfg["dim"]
         sd = state_dict if state_dict is not None else init_state_dict(model)
         self.encoder = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], self.S * self.n,
-                                      pack_for_device(model, sd), device=self.device)
+                                      pack_for_device(model, sd, crop_size=self.crop_size),
+                                      device=self.device, crop_size=self.crop_size)
         dev, S, n = self.device, self.S, self.n
         f32 = torch.float32
         self.particles = torch.zeros((S, 6, n), dtype=f32, device=dev)
         self._next = torch.zeros((S, 6, n), dtype=f32, device=dev)
         self.weights = torch.zeros((S, n), dtype=f32, device=dev)
-        self.patches = torch.empty((S * n * ops.N_PATCH, ops.PATCH_K), dtype=torch.bfloat16, device=dev)
+        self.patches = torch.empty((S * n * self.n_patch, ops.PATCH_K), dtype=torch.bfloat16, device=dev)
         self.emb = torch.empty((S * n, self.dim), dtype=f32, device=dev)
         self.logw = torch.empty((S, n), dtype=f32, device=dev)
         self.idx = torch.empty((S, n), dtype=torch.int32, device=dev)
@@ -65,9 +69,10 @@ class MultiStreamTracker:
                              float(np.float32(0.1 * sc))))
             boxes[s] = torch.tensor([x + 0.5 * w, y + 0.5 * h, w, h])
         boxes = boxes.to(self.device)
-        tp = torch.empty((self.S * ops.N_PATCH, ops.PATCH_K), dtype=torch.bfloat16, device=self.device)
+        P = self.n_patch
+        tp = torch.empty((self.S * P, ops.PATCH_K), dtype=torch.bfloat16, device=self.device)
         for s in range(self.S):
-            ops.crop_boxes(frames[s], boxes[s:s + 1], tp[s * ops.N_PATCH:(s + 1) * ops.N_PATCH])
+            ops.crop_boxes(frames[s], boxes[s:s + 1], tp[s * P:(s + 1) * P], crop_size=self.crop_size)
         self.encoder.forward(tp, self.S, self.templates)
         for s, bb in enumerate(bboxes):
             x, y, w, h = [np.float32(v) for v in bb]
@@ -82,12 +87,12 @@ class MultiStreamTracker:
             raise RuntimeError("call init(frames, bboxes) before step(frames)")
         frames = self._frames(frames)
         self.frame_idx += 1
-        t, n = self.frame_idx, self.n
+        t, n, P = self.frame_idx, self.n, self.n_patch
         for s in range(self.S):
             sp, sv, _ = self.sig[s]
             ops.propagate(self.particles[s], sp, sv, self.sigma_scale, self.seed, t, self.stream_ids[s], 0)
             ops.crop_state(frames[s], self.particles[s], self.w0[s], self.h0[s],
-                           self.patches[s * n * ops.N_PATCH:(s + 1) * n * ops.N_PATCH])
+                           self.patches[s * n * P:(s + 1) * n * P], crop_size=self.crop_size)
         self.encoder.forward(self.patches, self.S * n, self.emb)        # all streams, one batch
         self._stats.zero_()
         for s in range(self.S):

@@ -11,9 +11,22 @@ import torch
 
 from . import _lib
 
-N_PATCH = 196
+N_PATCH = 196        # patches per crop at the default crop size (224)
 PATCH_K = 768
 TOKENS = 197
+CROP = 224
+
+
+def n_patch(crop_size: int = CROP) -> int:
+    """Patches per crop: (S/16)^2 for a crop size S that is a multiple of 16 in [16, 224]."""
+    s = int(crop_size)
+    if s < 16 or s > CROP or s % 16:
+        raise ValueError(f"crop size must be a multiple of 16 in [16, {CROP}], got {crop_size}")
+    return (s // 16) ** 2
+
+
+def n_tokens(crop_size: int = CROP) -> int:
+    return n_patch(crop_size) + 1
 
 
 def _stream() -> int:
@@ -91,34 +104,39 @@ def resample_uniform(seed, frame_idx, stream_id=0) -> float:
 
 
 # ---- crop --------------------------------------------------------------------------------------
-def crop_state(frame, state, w0, h0, out=None, dtype=torch.bfloat16):
+def crop_state(frame, state, w0, h0, out=None, dtype=torch.bfloat16, crop_size=CROP):
     _dev(frame, torch.uint8)
     _dev(state, torch.float32)
     H, W, _ = frame.shape
     n = state.shape[1]
+    rows = n * n_patch(crop_size)
     if out is None:
-        out = torch.empty((n * N_PATCH, PATCH_K), dtype=dtype, device=frame.device)
+        out = torch.empty((rows, PATCH_K), dtype=dtype, device=frame.device)
+    assert out.is_contiguous() and out.numel() >= rows * PATCH_K
     _lib.check(_lib.load().vpf_crop_state(frame.data_ptr(), H, W, state.data_ptr(), n,
                                           state.stride(0), w0, h0, out.data_ptr(),
-                                          _dtype_code(out.dtype), _stream()), "vpf_crop_state")
+                                          _dtype_code(out.dtype), crop_size, _stream()),
+               "vpf_crop_state")
     return out
 
 
-def crop_boxes(frame, boxes, out=None, dtype=torch.bfloat16):
+def crop_boxes(frame, boxes, out=None, dtype=torch.bfloat16, crop_size=CROP):
     _dev(frame, torch.uint8)
     _dev(boxes, torch.float32)
     H, W, _ = frame.shape
     n = boxes.shape[0]
+    rows = n * n_patch(crop_size)
     if out is None:
-        out = torch.empty((n * N_PATCH, PATCH_K), dtype=dtype, device=frame.device)
+        out = torch.empty((rows, PATCH_K), dtype=dtype, device=frame.device)
+    assert out.is_contiguous() and out.numel() >= rows * PATCH_K
     _lib.check(_lib.load().vpf_crop_boxes(frame.data_ptr(), H, W, boxes.data_ptr(), n,
-                                          out.data_ptr(), _dtype_code(out.dtype), _stream()),
-               "vpf_crop_boxes")
+                                          out.data_ptr(), _dtype_code(out.dtype), crop_size,
+                                          _stream()), "vpf_crop_boxes")
     return out
 
 
 # ---- ViT stages (test hooks) ---------------------------------------------------------------------
-def gemm_bf16(a, w, bias, mode, out=None, pos=None):
+def gemm_bf16(a, w, bias, mode, out=None, pos=None, patches_per_crop=N_PATCH):
     """C = A[M,K] @ W[N,K]^T with epilogue `mode` (see include/vpf.h)."""
     _dev(a, torch.bfloat16); _dev(w, torch.bfloat16); _dev(bias, torch.float32)
     M, K = a.shape
@@ -127,7 +145,8 @@ def gemm_bf16(a, w, bias, mode, out=None, pos=None):
         assert mode in (0, 1)
         out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
     _lib.check(_lib.load().vpf_gemm_bf16(a.data_ptr(), w.data_ptr(), bias.data_ptr(),
-                                         out.data_ptr(), _lib.ptr(pos), M, N, K, mode, _stream()),
+                                         out.data_ptr(), _lib.ptr(pos), M, N, K, mode,
+                                         patches_per_crop, _stream()),
                "vpf_gemm_bf16")
     return out
 
@@ -141,12 +160,12 @@ def layernorm(x, gamma, beta):
     return out
 
 
-def attention(qkv, n_crops, heads):
+def attention(qkv, n_crops, heads, tokens=TOKENS):
     _dev(qkv, torch.bfloat16)
     D = heads * 64
-    assert qkv.shape == (n_crops * TOKENS, 3 * D)
-    out = torch.empty((n_crops * TOKENS, D), dtype=torch.bfloat16, device=qkv.device)
-    _lib.check(_lib.load().vpf_attention(qkv.data_ptr(), out.data_ptr(), n_crops, heads,
+    assert qkv.shape == (n_crops * tokens, 3 * D)
+    out = torch.empty((n_crops * tokens, D), dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(_lib.load().vpf_attention(qkv.data_ptr(), out.data_ptr(), n_crops, heads, tokens,
                                          _stream()), "vpf_attention")
     return out
 
@@ -185,15 +204,21 @@ class VitEncoder:
     """Owns the opaque vpf_vit handle, the packed device weights and the workspace tensor."""
 
     def __init__(self, dim, depth, heads, max_crops, packed_weights, device="cuda",
-                 dtype=torch.bfloat16):
+                 dtype=torch.bfloat16, crop_size=CROP):
         lib = _lib.load()
         self._lib = lib
         self.dim, self.depth, self.heads, self.max_crops = dim, depth, heads, max_crops
         self.dtype = dtype
+        self.crop_size = int(crop_size)
+        self.tokens = n_tokens(crop_size)
+        if tuple(packed_weights[3].shape) != (self.tokens, dim):
+            raise ValueError(f"pos_embed is {tuple(packed_weights[3].shape)}, crop size "
+                             f"{crop_size} needs ({self.tokens}, {dim}): pack the weights with "
+                             "pack_for_device(..., crop_size=...)")
         wd = {t.dtype for t in packed_weights if t.dtype in (torch.bfloat16, torch.float16)}
         if wd != {dtype}:
             raise ValueError(f"packed GEMM weights are {wd}, encoder operand type is {dtype}")
-        self.cfg = _lib.VitConfig(dim, depth, heads, max_crops, _dtype_code(dtype))
+        self.cfg = _lib.VitConfig(dim, depth, heads, max_crops, _dtype_code(dtype), self.crop_size)
         self._h = C.c_void_p()
         _lib.check(lib.vpf_vit_create(C.byref(self._h), C.byref(self.cfg)), "vpf_vit_create")
         self.weights = [t.to(device).contiguous() for t in packed_weights]   # keep alive

@@ -38,13 +38,17 @@ class Tracker:
     def __init__(self, model="vit_base_patch16_224", n_particles=4096, seed=0, device="cuda",
                  dtype=torch.bfloat16, tau=0.1, sigma_pos=None, sigma_vel=None, sigma_scale=0.01,
                  sigma_init=None, state_dict=None, process_group=None, stream_id=0,
-                 encoder=None, cuda_graph=False):
+                 encoder=None, cuda_graph=False, crop_size=224):
         if not torch.cuda.is_available():
             raise RuntimeError("Tracker needs a CUDA device: the hot path has no CPU fallback")
         if dtype not in (torch.bfloat16, torch.float16):
             raise ValueError("the sm_100a ViT path takes bf16 (default) or fp16 operands, "
                              "fp32 accumulation")
         self.dtype = dtype
+        # 224 = the oracle's default; a smaller multiple of 16 is the "native-resolution crops"
+        # option of SURVEY.md section 8f-2 (e.g. 64 -> 17 tokens per particle instead of 197)
+        self.crop_size = int(crop_size)
+        self.n_patch = ops.n_patch(self.crop_size)
         if model not in VIT_CONFIGS:
             raise ValueError(f"unknown model {model!r}; choose from {sorted(VIT_CONFIGS)}")
         self.model = model
@@ -66,16 +70,17 @@ class Tracker:
         if encoder is None:
             sd = state_dict if state_dict is not None else init_state_dict(model)
             encoder = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], self.n,
-                                     pack_for_device(model, sd, dtype), device=self.device,
-                                     dtype=dtype)
+                                     pack_for_device(model, sd, dtype, self.crop_size),
+                                     device=self.device, dtype=dtype, crop_size=self.crop_size)
         assert encoder.max_crops >= self.n and encoder.dtype == dtype
+        assert encoder.crop_size == self.crop_size
         self.encoder = encoder
         dev, n, R = self.device, self.n, self.world
         f32, f64 = torch.float32, torch.float64
         self.particles = torch.zeros((6, n), dtype=f32, device=dev)
         self._next = torch.zeros((6, n), dtype=f32, device=dev)
         self.weights = torch.full((n,), 1.0 / self.n_global, dtype=f32, device=dev)
-        self.patches = torch.empty((n * ops.N_PATCH, ops.PATCH_K), dtype=dtype, device=dev)
+        self.patches = torch.empty((n * self.n_patch, ops.PATCH_K), dtype=dtype, device=dev)
         self.emb = torch.empty((n, self.dim), dtype=f32, device=dev)
         self.logw = torch.empty((n,), dtype=f32, device=dev)
         self.idx = torch.empty((n,), dtype=torch.int32, device=dev)
@@ -116,7 +121,7 @@ class Tracker:
         self.sigma_scale = float(np.float32(ss))
         self.sigma_init = float(np.float32(0.1 * scale if si is None else si))
         self._tbox.copy_(torch.tensor([[x + 0.5 * w, y + 0.5 * h, w, h]], dtype=torch.float32))
-        tp = ops.crop_boxes(frame, self._tbox, dtype=self.dtype)
+        tp = ops.crop_boxes(frame, self._tbox, dtype=self.dtype, crop_size=self.crop_size)
         self.encoder.forward(tp, 1, self.template.view(1, -1))
         cx = float(np.float32(np.float32(x) + np.float32(0.5) * np.float32(w)))
         cy = float(np.float32(np.float32(y) + np.float32(0.5) * np.float32(h)))
@@ -145,7 +150,7 @@ class Tracker:
                       self.stream_id, self.id_offset)
         # a4 crop, a5 ViT
         if _emb is None:
-            ops.crop_state(frame, st, self.w0, self.h0, self.patches)
+            ops.crop_state(frame, st, self.w0, self.h0, self.patches, crop_size=self.crop_size)
             self.encoder.forward(self.patches, self.n, self.emb)
             emb = self.emb
         else:
@@ -191,12 +196,13 @@ class Tracker:
                 "seed": self.seed, "stream_id": self.stream_id, "w0": self.w0, "h0": self.h0,
                 "sigmas": (self.sigma_pos, self.sigma_vel, self.sigma_scale, self.sigma_init),
                 "model": self.model, "n_particles": self.n_global, "rank": self.rank,
-                "world": self.world}
+                "world": self.world, "crop_size": self.crop_size}
 
     def load_state_dict(self, sd: dict) -> None:
-        if (sd["model"], sd["n_particles"], sd["rank"], sd["world"]) != \
-                (self.model, self.n_global, self.rank, self.world):
-            raise ValueError("checkpoint was taken with a different model / particle count / sharding")
+        if (sd["model"], sd["n_particles"], sd["rank"], sd["world"], sd.get("crop_size", 224)) != \
+                (self.model, self.n_global, self.rank, self.world, self.crop_size):
+            raise ValueError("checkpoint was taken with a different model / particle count / "
+                             "sharding / crop size")
         self.particles.copy_(sd["particles"])
         self.weights.copy_(sd["weights"])
         self.template.copy_(sd["template"])
@@ -213,7 +219,8 @@ class Tracker:
         ops.frame_advance(self._fidx)
         ops.propagate_dev(st, self.sigma_pos, self.sigma_vel, self.sigma_scale, self.seed,
                           self._fidx, self.stream_id, self.id_offset)
-        ops.crop_state(self._frame_buf, st, self.w0, self.h0, self.patches)
+        ops.crop_state(self._frame_buf, st, self.w0, self.h0, self.patches,
+                       crop_size=self.crop_size)
         self.encoder.forward(self.patches, self.n, self.emb)
         ops.loglik(self.emb, self.template, self.tau, self.logw, xch.max_local)
         ops.sumexp(self.logw, xch.max_all, xch.sum_local)

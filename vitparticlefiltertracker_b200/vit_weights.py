@@ -19,11 +19,31 @@ TOKENS = 197
 WEIGHT_SEED = 1234
 
 
-def flops_per_crop(model: str) -> float:
-    """Full forward, 2 FLOP/MAC, no padding: 2*196*768*D + L*(24*197*D^2 + 4*197^2*D)."""
+def flops_per_crop(model: str, crop_size: int = 224) -> float:
+    """Full forward, 2 FLOP/MAC, no padding: 2*P*768*D + L*(24*T*D^2 + 4*T^2*D) with
+    P = (crop_size/16)^2 patches and T = P + 1 tokens (196 / 197 at the default 224)."""
     c = VIT_CONFIGS[model]
     d, l = c["dim"], c["depth"]
-    return 2.0 * 196 * 768 * d + l * (24.0 * TOKENS * d * d + 4.0 * TOKENS * TOKENS * d)
+    p = (crop_size // 16) ** 2
+    t = p + 1
+    return 2.0 * p * 768 * d + l * (24.0 * t * d * d + 4.0 * t * t * d)
+
+
+def resample_pos_embed(pos_embed: torch.Tensor, grid: int) -> torch.Tensor:
+    """[1, 1+g0*g0, D] -> [1, 1+grid*grid, D]: what timm applies to `vit_*_patch16_224` weights when
+    the input size changes (class-token row kept; grid rows resized bicubic, antialias, fp32).
+    One-time host-side weight preprocessing, outside the per-frame path."""
+    n_tok, d = pos_embed.shape[1], pos_embed.shape[2]
+    g0 = int(round((n_tok - 1) ** 0.5))
+    if g0 * g0 + 1 != n_tok:
+        raise ValueError("pos_embed must be [1, 1+g*g, D]")
+    if grid == g0:
+        return pos_embed
+    pe = pos_embed.detach().to(torch.float32).cpu()
+    g = pe[:, 1:].reshape(1, g0, g0, d).permute(0, 3, 1, 2)
+    g = torch.nn.functional.interpolate(g, size=(grid, grid), mode="bicubic", antialias=True,
+                                        align_corners=False)
+    return torch.cat([pe[:, :1], g.permute(0, 2, 3, 1).reshape(1, grid * grid, d)], dim=1)
 
 
 def _block_keys(i):
@@ -63,15 +83,17 @@ def init_state_dict(model: str, seed: int = WEIGHT_SEED) -> dict:
     return sd
 
 
-def pack_for_device(model: str, sd: dict, dtype=torch.bfloat16) -> list:
+def pack_for_device(model: str, sd: dict, dtype=torch.bfloat16, crop_size: int = 224) -> list:
     """timm state_dict -> list of CPU tensors in libvpf pointer order: GEMM weights in the 16-bit
-    operand type (`dtype`: bf16 or fp16) [out][in] (the K-major B operand), everything else fp32."""
+    operand type (`dtype`: bf16 or fp16) [out][in] (the K-major B operand), everything else fp32.
+    `crop_size` < 224 resamples pos_embed to the (crop_size/16)^2 grid."""
     c = VIT_CONFIGS[model]
     d, depth = c["dim"], c["depth"]
+    pos = resample_pos_embed(sd["pos_embed"], crop_size // 16)
     f32 = lambda t: t.detach().to(torch.float32).contiguous()
     bf = lambda t: t.detach().to(torch.float32).to(dtype).contiguous()
     out = [bf(sd["patch_embed.proj.weight"].reshape(d, 768)), f32(sd["patch_embed.proj.bias"]),
-           f32(sd["cls_token"].reshape(d)), f32(sd["pos_embed"].reshape(TOKENS, d))]
+           f32(sd["cls_token"].reshape(d)), f32(pos.reshape(pos.shape[1], d))]
     for i in range(depth):
         for key in _block_keys(i):
             t = sd[key]
