@@ -15,6 +15,11 @@ e2e    = the same through the public API with HOST frames: pinned host -> device
 roofline = the tcgen05 GEMM family (qkv/proj/fc1/fc2), timed live with CUDA events inside a
          sustained loop, against MEASURED_PEAKS.json's sustained bf16 figure.
 cpu_baseline = the CPU oracle (a port: the upstream repo is a README only) on a bounded sample.
+native_resolution = (N=1 only, informative, measured after everything above) the same workload
+         at crop size 64 -- SURVEY.md section 8f-2 "native-resolution crops": 17 tokens per
+         particle instead of 197, position embedding resampled, oracle revised to match
+         (OracleTracker(crop_size=64)).  It is NOT the headline: `value`, `e2e`, `roofline` stay
+         on the oracle's default 224-pixel crops.
 """
 from __future__ import annotations
 
@@ -286,6 +291,36 @@ def hbm_kernels(dev, trk, frame, peaks, iters=10):
     return out
 
 
+def native_resolution_point(dev, frames_dev, frames_host, gt, op_dtype, crop_size=64, steps=20,
+                            warmup=4):
+    """BASELINE configs[2] at the 'native-resolution' crop size (see the module docstring)."""
+    from vitparticlefiltertracker_b200 import Tracker, flops_per_crop
+    n = PARTICLES_PER_GPU
+    trk = Tracker(MODEL, n, seed=0, device=dev, dtype=op_dtype, crop_size=crop_size)
+    trk.init(frames_dev[0], gt[0])
+    res = {}
+    for name, src in (("resident", frames_dev), ("e2e_host_frames", frames_host)):
+        for i in range(warmup):
+            trk.step(src[1 + i % (CLIP_FRAMES - 1)])
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            trk.step(src[1 + (warmup + i) % (CLIP_FRAMES - 1)])
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / steps
+        res[name] = {"ms_per_step": ms, "frames_per_s": 1e3 / ms,
+                     "particle_updates_per_s": n * 1e3 / ms}
+    fl = flops_per_crop(MODEL, crop_size)
+    res.update({"crop_size": crop_size, "tokens_per_particle": (crop_size // 16) ** 2 + 1,
+                "gflop_per_particle_update": fl / 1e9, "steps": steps,
+                "step_tflops": n * fl / (res["resident"]["ms_per_step"] / 1e3) / 1e12,
+                "note": "informative operating point, not the headline: oracle revision "
+                        "OracleTracker(crop_size=64), parity in tests/test_gpu_cropsize.py"})
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -293,6 +328,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-native", action="store_true",
+                    help="skip the informative crop-size-64 operating point")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
                     help="16-bit operand type of the encoder (fp32 accumulation either way)")
     args = ap.parse_args()
@@ -363,6 +400,9 @@ def main():
     roof, gemm_ms = gemm_roofline(dev, trk.n * 197, trk.dim, peaks) if rank == 0 else (None, 0.0)
     hbm = hbm_kernels(dev, trk, frames_dev[1], peaks) if rank == 0 else None
     stages = stage_times(dev, trk, frames_dev[1]) if rank == 0 else None
+    native = None
+    if n_gpus == 1 and not args.no_native:
+        native = native_resolution_point(dev, frames_dev, frames_host, gt, op_dtype)
     barrier()
 
     tracking = {"mean_iou_vs_ground_truth": float(np.mean(ious[: args.warmup + args.steps])),
@@ -391,6 +431,8 @@ def main():
             "roofline": roof, "hbm_kernels": hbm, "stages_ms": stages, "tracking": tracking,
             "clocks": clocks,
         }
+        if native is not None:
+            line["native_resolution"] = native
         if n_gpus == 1 and not args.no_cpu_baseline:
             n_sample = 32
             v, sec, threads = cpu_oracle_run(2, 1, n_sample, frames[:4], gt[:4])

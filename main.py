@@ -37,7 +37,8 @@ def main(path="config.yaml"):
                   seed=cfg.get("seed", 0), tau=cfg.get("tau", 0.1), sigma_pos=cfg.get("sigma_pos"),
                   sigma_vel=cfg.get("sigma_vel"), sigma_scale=cfg.get("sigma_scale", 0.01),
                   sigma_init=cfg.get("sigma_init"), state_dict=sd, dtype=dtype,
-                  cuda_graph=bool(cfg.get("cuda_graph", False)))
+                  cuda_graph=bool(cfg.get("cuda_graph", False)),
+                  crop_size=int(cfg.get("crop_size", 224)))
     trk.init(np.ascontiguousarray(frames[0]), bbox)
     for f in range(1, len(frames)):
         t0 = time.perf_counter()

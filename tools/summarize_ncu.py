@@ -18,7 +18,7 @@ UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 TIME = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
 
-def launches(path):
+def launches(path, tag="r01", head=None):
     rows = [r for r in csv.reader(open(path)) if len(r) > 5]
     hdr = rows[0]
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
@@ -29,11 +29,11 @@ def launches(path):
     tot = sum(v[1] for v in agg.values())
     lines = [f"{k:64s} n={v[0]:4d} total={v[1] / 1e6:9.3f} ms share={v[1] / tot * 100:5.1f}% "
              f"avg={v[1] / v[0] / 1e3:9.1f} us" for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])]
-    head = ("ncu --metrics gpu__time_duration.sum --clock-control none -s 385 -c 300, bench.py --steps 2 "
-            "--warmup 3 (1xB200, ViT-B/16, N=4096)\nper-launch times are cold-cache and serialised at "
-            "full clocks: compare SHARES with bench.py's share_of_step\n\n")
-    open("profiles/launches_r01_summary.txt", "w").write(head + "\n".join(lines) + "\n")
-    open("profiles/launches_r01.csv", "w").write(open(path).read())
+    head = head or ("ncu --metrics gpu__time_duration.sum --clock-control none -s 385 -c 300, bench.py --steps 2 "
+                    "--warmup 3 (1xB200, ViT-B/16, N=4096)\nper-launch times are cold-cache and serialised at "
+                    "full clocks: compare SHARES with bench.py's share_of_step\n\n")
+    open(f"profiles/launches_{tag}_summary.txt", "w").write(head + "\n".join(lines) + "\n")
+    open(f"profiles/launches_{tag}.csv", "w").write(open(path).read())
     print("\n".join(lines[:8]))
 
 
@@ -71,6 +71,9 @@ def gemm(path):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 3 and sys.argv[2] == "--tag":     # launch list of another workload
+        launches(sys.argv[1], sys.argv[3], sys.argv[4] + "\n\n" if len(sys.argv) > 4 else None)
+        sys.exit(0)
     launches(sys.argv[1])
     if len(sys.argv) > 2:
         gemm(sys.argv[2])
