@@ -299,14 +299,22 @@ def native_resolution_point(dev, frames_dev, frames_host, gt, op_dtype, crop_siz
     trk = Tracker(MODEL, n, seed=0, device=dev, dtype=op_dtype, crop_size=crop_size)
     trk.init(frames_dev[0], gt[0])
     res = {}
-    for name, src in (("resident", frames_dev), ("e2e_host_frames", frames_host)):
+    from vitparticlefiltertracker_b200 import FrameIngest, track
+    ingest = FrameIngest(tuple(frames_host[0].shape), device=dev)
+    for name, src in (("resident", frames_dev), ("e2e_host_frames", frames_host),
+                      ("e2e_host_frames_prefetched", frames_host)):
         for i in range(warmup):
             trk.step(src[1 + i % (CLIP_FRAMES - 1)])
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        for i in range(steps):
-            trk.step(src[1 + (warmup + i) % (CLIP_FRAMES - 1)])
+        seq = (src[1 + (warmup + i) % (CLIP_FRAMES - 1)] for i in range(steps))
+        if name.endswith("prefetched"):          # pinned double-buffered upload beside the step
+            for _ in track(trk, seq, ingest):
+                pass
+        else:
+            for f in seq:
+                trk.step(f)
         e.record()
         torch.cuda.synchronize()
         ms = s.elapsed_time(e) / steps

@@ -135,3 +135,25 @@ def test_fp16_operand_mode_is_closer_to_the_fp32_oracle():
     relw = np.abs(trk.weights.cpu().numpy() / ora.last["w"] - 1).max()
     print(f"fp16 tracker: |dcos| {dcos:.2e}, weights rel {relw:.2e}")
     assert dcos < 6e-4 and relw < 6e-3
+
+
+def test_multistream_crop64_matches_single_stream_trackers():
+    """BASELINE configs[4] shape at the native-resolution crop size: S streams batched through one
+    encoder call must follow S independent Trackers bit for bit."""
+    from vitparticlefiltertracker_b200 import MultiStreamTracker, Tracker
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+    dev = cuda()
+    S, n, model = 3, 96, "vit_tiny_patch16_224"
+    clips = [make_clip("needle", 120, 160, 4, seed=s, target=(3, 60)) for s in range(S)]
+    frames = np.stack([c[0] for c in clips], axis=1)                        # [F,S,H,W,3]
+    mst = MultiStreamTracker(S, model, n, seed=0, crop_size=64)
+    mst.init(frames[0], [c[1][0] for c in clips])
+    singles = [Tracker(model, n, seed=0, stream_id=s, crop_size=64) for s in range(S)]
+    for s, t in enumerate(singles):
+        t.init(frames[0, s], clips[s][1][0])
+    for f in range(1, 4):
+        got = mst.step(frames[f])
+        for s, t in enumerate(singles):
+            want = t.step(frames[f, s])
+            assert torch.equal(mst.particles[s], t.particles), (f, s)
+            assert np.allclose(got[s].bbox, want.bbox, atol=1e-9) and got[s].frame_idx == f

@@ -112,3 +112,24 @@ def test_checkpoint_resume_reproduces_the_trajectory():
     b.load_state_dict(ckpt)
     got = [b.step(frames[t]) for t in range(4, 7)]
     assert got == ref and torch.equal(a.particles, b.particles)
+
+
+def test_frame_ingest_prefetch_matches_direct_stepping():
+    """FrameIngest / track(): pinned double-buffered upload on a side stream, frame t+1 in flight
+    while frame t is tracked -- same trajectory as stepping on the host frames directly."""
+    from vitparticlefiltertracker_b200 import FrameIngest, Tracker, track
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+    cuda()
+    frames, gt = make_clip("box", 224, 224, 9, seed=4, target=(48, 48))
+    a = Tracker("vit_tiny_patch16_224", 128, seed=1)
+    b = Tracker("vit_tiny_patch16_224", 128, seed=1, encoder=a.encoder)
+    a.init(frames[0], gt[0])
+    b.init(frames[0], gt[0])
+    ref = [a.step(frames[t]) for t in range(1, 9)]
+    ingest = FrameIngest(frames[0].shape, device=b.device, depth=2)
+    got = list(track(b, (frames[t] for t in range(1, 9)), ingest))
+    assert got == ref and torch.equal(a.particles, b.particles)
+    assert ingest.bytes_per_frame == 224 * 224 * 3
+    with pytest.raises(ValueError):
+        ingest.submit(np.zeros((10, 10, 3), np.uint8))
+    assert list(track(b, [], ingest)) == []

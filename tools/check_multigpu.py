@@ -25,12 +25,13 @@ def main():
     os.environ.setdefault("NCCL_DEBUG", "WARN")
     dist.init_process_group("nccl", device_id=dev)
     model, n, frames_n = "vit_tiny_patch16_224", 512, 5
+    crop_size = int(os.environ.get("VPF_CHECK_CROP_SIZE", "224"))
     frames, gt = make_clip("box", 224, 224, frames_n, seed=0, target=(48, 48))
-    sharded = Tracker(model, n, seed=7, device=dev, process_group=dist.group.WORLD)
+    sharded = Tracker(model, n, seed=7, device=dev, process_group=dist.group.WORLD, crop_size=crop_size)
     sharded.init(frames[0], gt[0])
     single = None
     if rank == 0:
-        single = Tracker(model, n, seed=7, device=dev)
+        single = Tracker(model, n, seed=7, device=dev, crop_size=crop_size)
         single.init(frames[0], gt[0])
     ok, report = True, []
     for f in range(1, frames_n):
@@ -51,7 +52,8 @@ def main():
                            "state": bool(same_b), "ess": s.ess})
             ok = ok and same_p and same_w and same_i and same_b
     if rank == 0:
-        print(json.dumps({"world": world, "n_particles": n, "bit_identical_to_single_gpu": ok,
+        print(json.dumps({"world": world, "n_particles": n, "crop_size": crop_size,
+                          "bit_identical_to_single_gpu": ok,
                           "frames": report}))
     dist.barrier()
     dist.destroy_process_group()

@@ -89,6 +89,7 @@ class Tracker:
         self._stats = torch.zeros((5,), dtype=f64, device=dev)
         self._tbox = torch.empty((1, 4), dtype=f32, device=dev)
         self.frame_idx = -1
+        self._pending = False
         # CUDA-graph mode (single GPU): the whole device side of a step is captured once and
         # replayed per frame; the frame counter and the resampling uniform then live on the device
         self.use_graph = bool(cuda_graph) and self.world == 1
@@ -129,16 +130,28 @@ class Tracker:
                            self.id_offset)
         self.weights.fill_(1.0 / self.n_global)
         self.frame_idx = 0
+        self._pending = False
         self._fidx.zero_()
         self._graph = None
 
     def step(self, frame, _u=None, _emb=None) -> State:
         """One tracked frame.  `_u` (resampling uniform) and `_emb` ([n,D] device embeddings) are
         test hooks that inject oracle quantities; every computation still runs in libvpf."""
+        self.step_begin(frame, _u, _emb)
+        return self.step_end()
+
+    def step_begin(self, frame, _u=None, _emb=None) -> None:
+        """Enqueues the whole device side of one frame on the current stream and returns without
+        waiting; `step_end()` reads the estimate back.  Lets a caller do host work (decode, stage the
+        next frame: `ingest.track`) while the GPU tracks this one."""
         if self.frame_idx < 0:
             raise RuntimeError("call init(frame, bbox) before step(frame)")
+        if self._pending:
+            raise RuntimeError("step_begin() called twice without step_end()")
         if self.use_graph and _u is None and _emb is None:
-            return self._step_graph(frame)
+            self._enqueue_graph(frame)
+            self._pending = True
+            return
         frame = self._to_device_frame(frame)
         self.frame_idx += 1
         if self.use_graph:
@@ -176,14 +189,20 @@ class Tracker:
         self.particles, self._next = self._next, self.particles
         self.propagated = self._next            # pre-resampling state of this frame (tests)
         self.last_u = u
-        # estimate: the only device->host read of the step
+        self._pending = True
+
+    def step_end(self) -> State:
+        """Estimate of the frame enqueued by `step_begin`: the only device->host read of a step."""
+        if not self._pending:
+            raise RuntimeError("step_end() without step_begin()")
+        self._pending = False
         s = self._stats.tolist()
         sw = s[0]
         cx, cy, sc = s[2] / sw, s[3] / sw, s[4] / sw
         ess = 1.0 / s[1] if s[1] > 0 else 0.0
         w = self.w0 * math.exp(sc)
         h = self.h0 * math.exp(sc)
-        return State((cx - 0.5 * w, cy - 0.5 * h, w, h), ess, t)
+        return State((cx - 0.5 * w, cy - 0.5 * h, w, h), ess, self.frame_idx)
 
     # -- checkpoint / resume -------------------------------------------------------------------
     def state_dict(self) -> dict:
@@ -231,7 +250,7 @@ class Tracker:
                          st, self._next, self.idx)
         st.copy_(self._next)                       # keeps every pointer of the graph static
 
-    def _step_graph(self, frame) -> State:
+    def _enqueue_graph(self, frame) -> None:
         if isinstance(frame, np.ndarray):
             frame = torch.from_numpy(frame)
         if frame.dtype != torch.uint8 or frame.dim() != 3 or frame.shape[2] != 3:
@@ -251,9 +270,3 @@ class Tracker:
         else:
             self._graph.replay()
         self.last_u = ops.resample_uniform(self.seed, self.frame_idx, self.stream_id)
-        s = self._stats.tolist()
-        sw = s[0]
-        cx, cy, sc = s[2] / sw, s[3] / sw, s[4] / sw
-        w, h = self.w0 * math.exp(sc), self.h0 * math.exp(sc)
-        return State((cx - 0.5 * w, cy - 0.5 * h, w, h), 1.0 / s[1] if s[1] > 0 else 0.0,
-                     self.frame_idx)
