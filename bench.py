@@ -127,7 +127,7 @@ def cpu_oracle_run(steps, warmup, n_sample, frames, gt):
     return n_sample * steps / dt, dt / steps, threads
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """--impl reference: the reference's CPU implementation of the path.  The upstream repo is a
     README only, so this is the oracle port (oracle/), with every host thread torch can use."""
     rank = int(os.environ.get("RANK", "0"))
@@ -152,7 +152,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frames_per_s_at_4096": v / PARTICLES_PER_GPU,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(n_gpus):
@@ -341,8 +341,17 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
                     help="16-bit operand type of the encoder (fp32 accumulation either way)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything a library writes to fd 1 (the NCCL version
+    # banner, for one) is sent to stderr, and the line itself goes out through a private copy
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
@@ -448,7 +457,7 @@ def main():
                 "value": v, "unit": UNIT, "cores": threads, "kind": "port",
                 "sample": f"OracleTracker (CPU PyTorch fp32): {n_sample} of {PARTICLES_PER_GPU} "
                           f"particles, 2 timed frames of the same clip ({sec:.1f} s/frame)"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
