@@ -65,12 +65,18 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        # address the GPU by UUID: with CUDA_VISIBLE_DEVICES set, nvidia-smi's index is not CUDA's
+        self.rows, self.proc, self.index = [], None, str(index)
+        try:
+            u = str(torch.cuda.get_device_properties(index).uuid)
+            self.index = u if u.startswith("GPU-") else "GPU-" + u
+        except Exception:
+            pass
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                ["nvidia-smi", "-i", self.index, f"--query-gpu={self.Q}",
                  "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)

@@ -257,3 +257,71 @@ def test_full_size_vit_base_4096_crop64_properties():
     assert _rel(emb, want) < 1e-2 and cos > 1 - 1e-3
     small = trk.encoder.forward(trk.patches.view(n, 16 * 768)[torch.from_numpy(sel).to(dev)].reshape(-1, 768).contiguous(), len(sel)).cpu()
     assert torch.equal(small, emb)
+
+
+def test_no_out_of_bounds_writes_with_canaries():
+    """compute-sanitizer is closed on this pool, so writes are fenced by hand: every output lives in
+    the middle of a sentinel-filled arena, and the sentinel on both sides must survive."""
+    from vitparticlefiltertracker_b200 import _lib, ops
+    dev = cuda()
+    lib = _lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    PAD = 4096
+    rng = np.random.default_rng(0)
+    frame = torch.from_numpy(rng.integers(0, 256, size=(97, 131, 3), dtype=np.uint8)).to(dev)
+
+    def arena(n_elems, dtype, fill):
+        a = torch.full((n_elems + 2 * PAD,), fill, dtype=dtype, device=dev)
+        return a, a[PAD:PAD + n_elems]
+
+    def intact(a, n_elems, fill):
+        return bool((a[:PAD] == fill).all()) and bool((a[PAD + n_elems:] == fill).all())
+
+    # crop, every grid parity, boxes that up-sample, down-sample and hang over the frame
+    boxes = torch.tensor([[60, 40, 30, 30], [5, 5, 200, 150], [128, 95, 64, 64], [60, 40, 9, 300]],
+                         dtype=torch.float32, device=dev)
+    for S in (16, 48, 64, 112, 224):
+        n_el = boxes.shape[0] * (S // 16) ** 2 * 768
+        a, out = arena(n_el, torch.bfloat16, 7.0)
+        _lib.check(lib.vpf_crop_boxes(frame.data_ptr(), 97, 131, boxes.data_ptr(), boxes.shape[0],
+                                      out.data_ptr(), _lib.DTYPE_BF16, S, stream), "vpf_crop_boxes")
+        torch.cuda.synchronize()
+        assert intact(a, n_el, 7.0), S
+        assert bool((out.float().abs() <= 1.0).all()), S          # every element was written
+    # attention: all three small-token kernels
+    heads, n = 3, 5
+    for tokens in (2, 17, 33, 64, 65, 150):
+        qkv = torch.randn(n * tokens, 3 * 64 * heads, device=dev).to(torch.bfloat16)
+        n_el = n * tokens * 64 * heads
+        a, out = arena(n_el, torch.bfloat16, 1000.0)
+        _lib.check(lib.vpf_attention(qkv.data_ptr(), out.data_ptr(), n, heads, tokens, stream),
+                   "vpf_attention")
+        torch.cuda.synchronize()
+        assert intact(a, n_el, 1000.0), tokens
+        assert bool((out.float().abs() < 100.0).all()), tokens
+    # patch-embed row remap (fp32 residual stream), 16 patches per crop
+    ncrop, D, P = 9, 192, 16
+    A = torch.randn(ncrop * P, 768, device=dev).to(torch.bfloat16)
+    Wt = (torch.randn(D, 768, device=dev) * 0.02).to(torch.bfloat16)
+    bias = torch.zeros(D, device=dev)
+    pos = torch.zeros(P + 1, D, device=dev)
+    n_el = ncrop * (P + 1) * D
+    a, X = arena(n_el, torch.float32, 55.0)
+    _lib.check(lib.vpf_gemm_bf16(A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), X.data_ptr(),
+                                 pos.data_ptr(), ncrop * P, D, 768, 3, P, stream), "vpf_gemm_bf16")
+    torch.cuda.synchronize()
+    assert intact(a, n_el, 55.0)
+    assert bool((X.view(ncrop, P + 1, D)[:, 0] == 55.0).all())     # CLS rows are not the GEMM's
+    # whole encoder at 17 tokens: workspace and embedding output fenced
+    from vitparticlefiltertracker_b200 import pack_for_device, init_state_dict
+    model = "vit_tiny_patch16_224"
+    cfg = VIT_CONFIGS[model]
+    enc = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], 6,
+                         pack_for_device(model, init_state_dict(model), crop_size=64), dev, crop_size=64)
+    patches = torch.randn(6 * 16, 768, device=dev).to(torch.bfloat16)
+    a, emb = arena(6 * cfg["dim"], torch.float32, -3.0)
+    ws_tail = enc.workspace[-8:].clone()
+    enc.forward(patches, 6, emb.view(6, cfg["dim"]))
+    torch.cuda.synchronize()
+    assert intact(a, 6 * cfg["dim"], -3.0) and torch.isfinite(emb).all()
+    assert torch.equal(enc.workspace[-8:], ws_tail)
