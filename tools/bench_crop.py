@@ -1,6 +1,5 @@
 """K1 (crop + resize + normalise + patchify) timed alone: achieved HBM GB/s on its algorithmic
-bytes (3*S*S*2 written per particle) for several box sizes.  VPF_CROP=v1 selects the previous
-non-separable kernel.  Usage: python tools/bench_crop.py [n_particles]"""
+bytes (3*S*S*2 written per particle) for several box sizes.  Usage: python tools/bench_crop.py [n_particles]"""
 import json
 import os
 import sys
@@ -29,7 +28,7 @@ def main():
     dev = torch.device("cuda")
     g = torch.Generator(device="cpu").manual_seed(0)
     frame = torch.randint(0, 256, (1080, 1920, 3), dtype=torch.uint8, generator=g).to(dev)
-    res = {"kernel": os.environ.get("VPF_CROP", "separable"), "n": n}
+    res = {"kernel": "crop_sep_kernel", "n": n}
     for S in (224, 64):
         patches = torch.empty(n * (S // 16) ** 2, 768, dtype=torch.bfloat16, device=dev)
         for box in (48, 96, 160, 224, 400):

@@ -4,27 +4,17 @@
 //
 // HBM-write bound by construction: 3*S*S bf16 written per particle (301 056 B at the default crop
 // size S = 224; S is a run-time multiple of 16, see SURVEY.md section 8f-2 "native-resolution
-// crops"); the uint8 frame (<= 6.2 MB) lives in L2.  One CTA produces two patch rows (32 x S
-// output pixels) of one crop:
-//   1. the particle box and the S horizontal taps (x0, frac) -- identical for every output
-//      row of the crop -- are staged in shared memory once per CTA;
-//   2. the source rows the CTA touches are copied to shared memory with coalesced 4-byte loads
-//      (falls back to direct global taps when the box is too large to stage);
-//   3. one warp writes one 16x16 patch per iteration as three 512-byte contiguous runs (one per
-//      channel), each lane producing 8 consecutive pixels (one 16-byte store per channel).
-// The arithmetic mirrors the oracle's fp32 operation order with explicit round-to-nearest
-// intrinsics (no FMA contraction), so the result equals bf16(oracle) bit for bit.
+// crops"); the uint8 frame (<= 6.2 MB) lives in L2.  The output is written directly in the
+// patch-embedding GEMM's A layout [crop][patch][c*256 + ky*16 + kx], so no im2col pass exists.
+// The arithmetic keeps the oracle's fp32 operation order with explicit round-to-nearest
+// operations (no FMA contraction), so the result equals bf16(oracle) bit for bit.
 #include "common.cuh"
-
-#include <stdlib.h>
 
 namespace vpf {
 
 static constexpr int kMaxCrop = 224;
 static constexpr int kPatch = 16;
 static constexpr int kPatchK = 768;
-static constexpr int kRowsPerCta = 2 * kPatch;            // 32 output rows = two patch rows
-static constexpr int kStageWords = 9 * 1024;              // 36 KB of staged source rows
 
 struct Box {
   float cx, cy, w, h;
@@ -35,137 +25,24 @@ __device__ __forceinline__ float sample_coord(float base, float step, int k, flo
   return fminf(fmaxf(x, 0.0f), hi);
 }
 
-template <bool kFromState>
-__global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ frame, int H, int W,
-                                                    const float* __restrict__ src, int n, int ld,
-                                                    float w0, float h0,
-                                                    __nv_bfloat16* __restrict__ out, bool f16,
-                                                    int S /* output crop size, multiple of 16 */) {
-  __shared__ uint32_t stage[kStageWords];
-  __shared__ float s_fx[kMaxCrop];
-  __shared__ int s_x0[kMaxCrop];
-  const int grid_p = S / kPatch;                         // patches per row / column
-  const int crop_patches = grid_p * grid_p;
-  const int crop = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  Box b;
-  if (kFromState) {
-    float es = expf(src[4 * (size_t)ld + crop]);
-    b.cx = src[crop];
-    b.cy = src[(size_t)ld + crop];
-    b.w = __fmul_rn(w0, es);
-    b.h = __fmul_rn(h0, es);
-  } else {
-    b.cx = src[crop * 4 + 0]; b.cy = src[crop * 4 + 1];
-    b.w = src[crop * 4 + 2];  b.h = src[crop * 4 + 3];
-  }
-  const float stepx = __fdiv_rn(b.w, (float)S), stepy = __fdiv_rn(b.h, (float)S);
-  const float basex = __fsub_rn(__fsub_rn(b.cx, __fmul_rn(0.5f, b.w)), 0.5f);
-  const float basey = __fsub_rn(__fsub_rn(b.cy, __fmul_rn(0.5f, b.h)), 0.5f);
-  const float xmax = (float)(W - 1), ymax = (float)(H - 1);
-  const float c255 = 2.0f / 255.0f;
-  const int i0 = blockIdx.y * kRowsPerCta;
-  const int n_rows = min(kRowsPerCta, S - i0);           // 32, or 16 for an odd last patch row
-  const int first_patch = 2 * blockIdx.y * grid_p;
-  const int n_patches = (n_rows / kPatch) * grid_p;
-
-  // ---- horizontal taps, shared by every output row ----
-  if (threadIdx.x < S) {
-    const float xs = sample_coord(basex, stepx, threadIdx.x, xmax);
-    const float x0f = floorf(xs);
-    s_fx[threadIdx.x] = __fsub_rn(xs, x0f);
-    s_x0[threadIdx.x] = (int)x0f;
-  }
-  // ---- source window of this CTA (coordinates are monotone in the output index) ----
-  const int y_lo = (int)floorf(sample_coord(basey, stepy, i0, ymax));
-  const int y_hi = min((int)floorf(sample_coord(basey, stepy, i0 + n_rows - 1, ymax)) + 1, H - 1);
-  const int x_lo = (int)floorf(sample_coord(basex, stepx, 0, xmax));
-  const int x_hi = min((int)floorf(sample_coord(basex, stepx, S - 1, xmax)) + 1, W - 1);
-  const int rows = y_hi - y_lo + 1;
-  const int row_bytes = (x_hi - x_lo + 1) * 3;
-  const int pitch = (row_bytes + 6) / 4 + 1;                  // words per staged row
-  const bool staged = rows * pitch <= kStageWords;
-  if (staged) {
-    const uintptr_t end = reinterpret_cast<uintptr_t>(frame) + (size_t)H * W * 3;
-    for (int idx = threadIdx.x; idx < rows * pitch; idx += 256) {
-      const int r = idx / pitch, wd = idx - r * pitch;
-      const uintptr_t g0 = reinterpret_cast<uintptr_t>(frame) + ((size_t)(y_lo + r) * W + x_lo) * 3;
-      const uintptr_t ga = (g0 & ~(uintptr_t)3) + (uintptr_t)wd * 4;   // 4-byte aligned word
-      uint32_t v = 0;
-      if (ga + 4 <= end) {
-        v = __ldg(reinterpret_cast<const uint32_t*>(ga));
-      } else {
-        for (int k = 0; k < 4; ++k)
-          if (ga + k < end) v |= (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(ga + k)) << (8 * k);
-      }
-      stage[idx] = v;
-    }
-  }
-  __syncthreads();
-  const uint8_t* sbytes = reinterpret_cast<const uint8_t*>(stage);
-  const int ky = lane >> 1, kx0 = (lane & 1) * 8;
-
-  for (int pl = warp; pl < n_patches; pl += 8) {
-    const int p = first_patch + pl;
-    const int py = p / grid_p, px = p - py * grid_p;
-    const int i = py * kPatch + ky;
-    const float ys = sample_coord(basey, stepy, i, ymax);
-    const float y0f = floorf(ys);
-    const float fy = __fsub_rn(ys, y0f);
-    const float gy = __fsub_rn(1.0f, fy);
-    const int y0 = (int)y0f, y1 = min(y0 + 1, H - 1);
-    const uint8_t* tap = staged ? sbytes : frame;
-    long long off0, off1;
-    if (staged) {
-      // a staged row starts at the 4-byte aligned address at or below its first pixel (x_lo)
-      const int sh0 = (int)((reinterpret_cast<uintptr_t>(frame) + ((size_t)y0 * W + x_lo) * 3) & 3);
-      const int sh1 = (int)((reinterpret_cast<uintptr_t>(frame) + ((size_t)y1 * W + x_lo) * 3) & 3);
-      off0 = (long long)(y0 - y_lo) * pitch * 4 + sh0 - x_lo * 3;
-      off1 = (long long)(y1 - y_lo) * pitch * 4 + sh1 - x_lo * 3;
-    } else {
-      off0 = (long long)y0 * W * 3;
-      off1 = (long long)y1 * W * 3;
-    }
-    __align__(16) uint16_t v[3][8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int j = px * kPatch + kx0 + e;
-      const float fx = s_fx[j];
-      const int x0 = s_x0[j], x1 = min(x0 + 1, W - 1);
-      const float gx = __fsub_rn(1.0f, fx);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float p00 = (float)tap[off0 + x0 * 3 + c], p01 = (float)tap[off0 + x1 * 3 + c];
-        float p10 = (float)tap[off1 + x0 * 3 + c], p11 = (float)tap[off1 + x1 * 3 + c];
-        float top = __fadd_rn(__fmul_rn(gx, p00), __fmul_rn(fx, p01));
-        float bot = __fadd_rn(__fmul_rn(gx, p10), __fmul_rn(fx, p11));
-        float val = __fadd_rn(__fmul_rn(gy, top), __fmul_rn(fy, bot));
-        v[c][e] = pack16(__fsub_rn(__fmul_rn(val, c255), 1.0f), f16);
-      }
-    }
-    __nv_bfloat16* dst = out + ((size_t)crop * crop_patches + p) * kPatchK + ky * kPatch + kx0;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      *reinterpret_cast<uint4*>(dst + c * 256) = *reinterpret_cast<const uint4*>(v[c]);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// Separable form (default).  One CTA = one patch row (16 x S output pixels) of one crop, 7 warps.
+// Separable bilinear.  One CTA = one patch row (16 x S output pixels) of one crop, 7 warps.
 // Bilinear interpolation as the oracle writes it is  val = gy*top + fy*bot  with
 //   top = gx*p[y0][x0] + fx*p[y0][x1],  bot = gx*p[y1][x0] + fx*p[y1][x1]:
 // `top` / `bot` depend only on (source row, output column), and with up-sampling (box smaller than
 // the crop, the tracker's normal case) the 16 output rows of a CTA touch only ~16*h/S + 2 source
 // rows.  So:
-//   phase A  the S horizontal taps (x0, frac) -> shared memory (as before)
+//   phase A  the particle box and the S horizontal taps (x0, frac) -> shared memory
 //   phase B  H[r][c][j] = gx*p[r][x0_j][c] + fx*p[r][x1_j][c] for every touched source row r, once,
 //            in fp32 with the oracle's operation order -> shared memory (<= h_cap rows)
 //   phase C  out[i][j][c] = gy_i*H[y0_i] + fy_i*H[y1_i], normalise, convert: packed fp32x2
 //            products, never-fused scalar sums, 16-byte shared loads, one warp per 16x16 patch
 //            writing three 512-byte runs.
 // Same roundings in the same order as the oracle => still bit-equal to bf16(oracle); about 8
-// instructions per output value instead of 20.  Patch rows that touch more than h_cap source rows (down-sampling: no row reuse to exploit)
-// stage the raw source window as bytes instead and interpolate per output, same arithmetic.
+// instructions per output value instead of the 20 of a per-output four-tap kernel.  Patch rows that
+// touch more than h_cap source rows (down-sampling: no row reuse to exploit) stage the raw source
+// window as bytes instead (coalesced 4-byte loads) and interpolate per output, same arithmetic;
+// windows too large even for that take their taps from global memory.
 static constexpr int kV2Threads = 224;                       // 7 warps: 14 patches in two rounds
 static constexpr int kHRowsMax = 20;                         // largest H-row budget a launch may ask for
 static constexpr int kHPitchMax = 3 * kMaxCrop + 4;          // floats per H row (+4: bank spread)
@@ -341,20 +218,10 @@ __global__ void __launch_bounds__(kV2Threads) crop_sep_kernel(const uint8_t* __r
   }
 }
 
-// VPF_CROP=v1 selects the previous (non-separable, 32-row) kernel for A/B measurements.
-static bool crop_use_sep() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VPF_CROP");
-    v = (e && e[0] == 'v' && e[1] == '1') ? 0 : 1;
-  }
-  return v == 1;
-}
-
 template <bool kFromState>
 static int launch_crop(const uint8_t* frame, int H, int W, const float* src, int n, int ld, float w0,
                        float h0, void* out, bool f16, int S, cudaStream_t stream) {
-  if (crop_use_sep()) {
+  {
     static bool attr[32] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -387,9 +254,6 @@ static int launch_crop(const uint8_t* frame, int H, int W, const float* src, int
     if (smem > h_cap * (3 * S + 4) * 4 || !kFromState) warps = kV2Threads / 32;
     crop_sep_kernel<kFromState><<<dim3(n, S / kPatch), warps * 32, smem, stream>>>(
         frame, H, W, src, n, ld, w0, h0, (__nv_bfloat16*)out, f16, S, h_cap, smem / 4);
-  } else {
-    crop_kernel<kFromState><<<dim3(n, (S + kRowsPerCta - 1) / kRowsPerCta), 256, 0, stream>>>(
-        frame, H, W, src, n, ld, w0, h0, (__nv_bfloat16*)out, f16, S);
   }
   VPF_LAUNCH_CHECK();
   return VPF_OK;
