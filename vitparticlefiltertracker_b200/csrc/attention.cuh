@@ -74,9 +74,11 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(smem);
   const uint32_t sK = sQ + kQRows * 128;
   const uint32_t sV = sK + kKeyRows * 128;
+  pdl_launch_dependents();
   const int head = blockIdx.x, crop = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t ld = (size_t)3 * D;
+  pdl_wait();
   const __nv_bfloat16* base = qkv + (size_t)crop * T * ld + head * kHeadDim;
 
   // ---- stage Q, K, V (rows >= T zero-filled) ----
@@ -238,9 +240,11 @@ attention_small_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
                        int n_pairs, int heads, int T, bool f16) {
   static_assert(KT == 32 || KT == 64, "padded token count");
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x * kSmallWarps + warp;
   if (pair >= n_pairs) return;                        // warp-uniform; no block barriers below
+  pdl_wait();
   const int crop = pair / heads, head = pair - crop * heads;
   const int D = heads * kHeadDim;
   const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(smem) + warp * SmallAttn<KT>::kWarpBytes;

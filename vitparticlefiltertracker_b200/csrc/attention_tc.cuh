@@ -150,6 +150,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* buf_empty = bars + 18;    // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int my_pairs = (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -169,6 +170,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================

@@ -50,6 +50,41 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---- Programmatic Dependent Launch ------------------------------------------------------------
+// Every kernel of the per-frame chain calls pdl_launch_dependents() first (the next kernel of the
+// stream may then be scheduled onto SMs as this grid drains, and run its prologue: barrier init,
+// tensor-memory allocation, descriptor prefetch) and pdl_wait() before its first global-memory
+// access (returns once the preceding grid has completed and its writes are visible), so the chain
+// keeps plain stream-order semantics.  Kernels launched without the attribute behave as before.
+// Measured (tools/bench_pdl.py, experiments/README.md): -7.5 % per frame for ViT-Ti / 256 particles
+// (short kernels, prologue-bound) but +2-3 % for the 4096-particle ViT-B shapes, so the attribute
+// is only set for small launches (pdl_for_rows).
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// rows = token (or patch) rows the launch works on.  VPF_PDL=0 / 1 forces the attribute off / on
+// for A/B runs; default: on up to kPdlMaxRows rows.  Defined in vit.cu.
+static constexpr int kPdlMaxRows = 65536;
+bool pdl_for_rows(long long rows);
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // 16-bit operand type of the encoder: bf16 (default) or fp16 (same tensor-core rate and bytes,
 // 3 more mantissa bits, less range) -- a run-time, warp-uniform flag.
 __device__ __forceinline__ uint32_t pack16x2(float a, float b, bool f16) {

@@ -75,9 +75,11 @@ __global__ void __launch_bounds__(kV2Threads) crop_sep_kernel(const uint8_t* __r
   extern __shared__ __align__(16) float s_h[];               // [h_cap][3][S] (+4 floats per row)
   __shared__ float s_fx[kMaxCrop];
   __shared__ int s_x0[kMaxCrop];
+  pdl_launch_dependents();
   const int grid_p = S / kPatch;
   const int crop = blockIdx.x, py = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_wait();                                                // the particle state is the motion kernel's output
   Box b;
   if (kFromState) {
     float es = expf(src[4 * (size_t)ld + crop]);
@@ -252,10 +254,11 @@ static int launch_crop(const uint8_t* frame, int H, int W, const float* src, int
     // thread helps with the copy
     int warps = (S / kPatch + 1) / 2 < 2 ? 2 : (S / kPatch + 1) / 2;
     if (smem > h_cap * (3 * S + 4) * 4 || !kFromState) warps = kV2Threads / 32;
-    crop_sep_kernel<kFromState><<<dim3(n, S / kPatch), warps * 32, smem, stream>>>(
-        frame, H, W, src, n, ld, w0, h0, (__nv_bfloat16*)out, f16, S, h_cap, smem / 4);
+    VPF_CUDA(launch_pdl(pdl_for_rows((long long)n * (S / kPatch) * (S / kPatch)),
+                        crop_sep_kernel<kFromState>, dim3(n, S / kPatch), dim3(warps * 32),
+                        (size_t)smem, stream, frame, H, W, src, n, ld, w0, h0,
+                        (__nv_bfloat16*)out, f16, S, h_cap, smem / 4));
   }
-  VPF_LAUNCH_CHECK();
   return VPF_OK;
 }
 

@@ -238,6 +238,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint64_t* epi_bar = full_bar + 32;   // [epilogue warp][2] "residual tile landed" (mode 2)
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
@@ -267,6 +268,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; operands are its output
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows / W half) ==========

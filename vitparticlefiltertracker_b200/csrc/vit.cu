@@ -27,6 +27,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool pdl_for_rows(long long rows) {
+  static int v = -2;                       // -1 auto, 0 off, 1 on
+  if (v == -2) {
+    const char* e = getenv("VPF_PDL");
+    v = !e ? -1 : (e[0] == '0' ? 0 : 1);
+  }
+  return v < 0 ? rows <= kPdlMaxRows : v == 1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA descriptors: the driver entry point is resolved at run time (libvpf.so links only the
 // static CUDA runtime, so it loads on machines without a driver).
@@ -164,13 +173,15 @@ static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   cfg.blockDim = dim3(EpiCfg<BLOCK_N, MODE>::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_for_rows(g.M) ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   CUtensorMap tmC = tmA;                       // modes 2 / 3 do not use it
   if (MODE <= 1 || MODE == kBiasResidualF32Tma) {
     int rc = make_store_map(&tmC, g.out, (uint64_t)g.M, (uint64_t)g.N, MODE == kBiasResidualF32Tma);
@@ -224,11 +235,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                          const float* __restrict__ beta,
                                                          OutT* __restrict__ out, int rows, int D,
                                                          bool f16 = false) {
+  pdl_launch_dependents();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int nvec = D >> 2;
   const float4* x4 = reinterpret_cast<const float4*>(x + (size_t)row * row_stride);
+  pdl_wait();
   float4 v[8];
   float sum = 0.f;
 #pragma unroll
@@ -273,11 +286,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
-// X[crop*197][:] = cls + pos[0]
+template <typename OutT>
+static cudaError_t launch_layernorm(int blocks, cudaStream_t s, const float* x, size_t row_stride,
+                                    const float* gamma, const float* beta, OutT* out, int rows,
+                                    int D, bool f16 = false) {
+  return launch_pdl(pdl_for_rows(rows), layernorm_kernel<OutT>, dim3(blocks), dim3(256), 0, s, x, row_stride, gamma, beta,
+                    out, rows, D, f16);
+}
+
+// X[crop*T][:] = cls + pos[0]
 __global__ void cls_init_kernel(float* __restrict__ X, const float* __restrict__ cls,
                                 const float* __restrict__ pos, int n_crops, int D, int T) {
+  pdl_launch_dependents();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_crops * D) return;
+  pdl_wait();       // X is still read by the previous forward's last kernels
   int crop = i / D, d = i - crop * D;
   X[(size_t)crop * T * D + d] = cls[d] + pos[d];
 }
@@ -300,9 +323,9 @@ static int launch_attention_small(const __nv_bfloat16* qkv, __nv_bfloat16* out, 
     VPF_CUDA(cudaFuncSetAttribute(attention_small_kernel<KT>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SmallAttn<KT>::kSmem));
   const int n_pairs = n_crops * heads;
-  attention_small_kernel<KT><<<(n_pairs + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32,
-                               SmallAttn<KT>::kSmem, s>>>(qkv, out, n_pairs, heads, tokens, f16 != 0);
-  VPF_LAUNCH_CHECK();
+  VPF_CUDA(launch_pdl(pdl_for_rows((long long)n_crops * tokens), attention_small_kernel<KT>, dim3((n_pairs + kSmallWarps - 1) / kSmallWarps),
+                      dim3(kSmallWarps * 32), (size_t)SmallAttn<KT>::kSmem, s, qkv, out, n_pairs,
+                      heads, tokens, f16 != 0));
   return VPF_OK;
 }
 
@@ -321,15 +344,15 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, attn::kSmemBytes));
     const int n_pairs = n_crops * heads;
     const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
-    attn::attention_tc_kernel<<<grid, attn::kThreads, attn::kSmemBytes, s>>>(*mq, *mkv, out, n_pairs,
-                                                                             heads, D, f16);
+    VPF_CUDA(launch_pdl(pdl_for_rows((long long)n_crops * tokens), attn::attention_tc_kernel, dim3(grid), dim3(attn::kThreads),
+                        (size_t)attn::kSmemBytes, s, *mq, *mkv, out, n_pairs, heads, D, f16));
   } else {
     static bool attr[32] = {};
     if (first_time_on_device(attr))
       VPF_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kAttnSmem));
-    attention_kernel<<<dim3(heads, n_crops), kAttnThreads, kAttnSmem, s>>>(qkv, out, D, tokens,
-                                                                          f16 != 0);
+    VPF_CUDA(launch_pdl(pdl_for_rows((long long)n_crops * tokens), attention_kernel, dim3(heads, n_crops), dim3(kAttnThreads),
+                        (size_t)kAttnSmem, s, qkv, out, D, tokens, f16 != 0));
   }
   VPF_LAUNCH_CHECK();
   return VPF_OK;
@@ -340,9 +363,11 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_
 // Xc[crop][:] = X[crop*197][:]
 __global__ void gather_cls_kernel(const float* __restrict__ X, float* __restrict__ Xc, int n_crops,
                                   int D, int T) {
+  pdl_launch_dependents();
   int i = blockIdx.x * blockDim.x + threadIdx.x;     // float4 index
   const int nv = D >> 2;
   if (i >= n_crops * nv) return;
+  pdl_wait();
   int crop = i / nv, v = i - crop * nv;
   reinterpret_cast<float4*>(Xc)[i] =
       reinterpret_cast<const float4*>(X + (size_t)crop * T * D)[v];
@@ -355,11 +380,13 @@ __global__ void __launch_bounds__(256) cls_attention_kernel(const __nv_bfloat16*
                                                             __nv_bfloat16* __restrict__ o,
                                                             int n_pairs, int heads, bool f16,
                                                             int T) {
+  pdl_launch_dependents();
   const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (pair >= n_pairs) return;
   const int crop = pair / heads, head = pair - crop * heads;
   const int D = heads * kHeadDim;
+  pdl_wait();
   float qf[kHeadDim];
   {
     const uint4* q4 = reinterpret_cast<const uint4*>(q + (size_t)crop * D + head * kHeadDim);
@@ -586,8 +613,7 @@ static int run_block(vpf_vit* h, const LayerW& w, int n, cudaStream_t s) {
   const int f16 = h->cfg.dtype == VPF_DTYPE_F16;
   const int ln_blocks = (M + 7) / 8;
   int rc;
-  layernorm_kernel<__nv_bfloat16><<<ln_blocks, 256, 0, s>>>(h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0);
-  VPF_LAUNCH_CHECK();
+  VPF_CUDA(launch_layernorm<__nv_bfloat16>(ln_blocks, s, h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0));
   {
     GemmArgs g{M, 3 * D, D, w.qkv_b, h->big, nullptr};
       g.f16 = f16;
@@ -599,8 +625,7 @@ static int run_block(vpf_vit* h, const LayerW& w, int n, cudaStream_t s) {
       g.f16 = f16;
     if ((rc = launch_gemm(h->a_xn, w.m_proj, g, kBiasResidualF32, s))) return rc;
   }
-  layernorm_kernel<__nv_bfloat16><<<ln_blocks, 256, 0, s>>>(h->X, D, w.ln2_g, w.ln2_b, h->Xn, M, D, f16 != 0);
-  VPF_LAUNCH_CHECK();
+  VPF_CUDA(launch_layernorm<__nv_bfloat16>(ln_blocks, s, h->X, D, w.ln2_g, w.ln2_b, h->Xn, M, D, f16 != 0));
   {
     GemmArgs g{M, 4 * D, D, w.fc1_b, h->big, nullptr};
       g.f16 = f16;
@@ -637,8 +662,7 @@ static int run_last_block_cls(vpf_vit* h, const LayerW& w, int n, float* emb, cu
   const int f16 = h->cfg.dtype == VPF_DTYPE_F16;
   const ClsBufs c = cls_bufs(h, n);
   int rc;
-  layernorm_kernel<__nv_bfloat16><<<(M + 7) / 8, 256, 0, s>>>(h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0);
-  VPF_LAUNCH_CHECK();
+  VPF_CUDA(launch_layernorm<__nv_bfloat16>((M + 7) / 8, s, h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0));
   {  // K, V for every token: rows [D, 3D) of the fused qkv weight
     GemmArgs g{M, 2 * D, D, w.qkv_b + D, h->big, nullptr};
       g.f16 = f16;
@@ -649,17 +673,16 @@ static int run_last_block_cls(vpf_vit* h, const LayerW& w, int n, float* emb, cu
       g.f16 = f16;
     if ((rc = launch_gemm(h->a_xn_cls, h->m_q_last, g, kBiasBf16, s))) return rc;
   }
-  cls_attention_kernel<<<(n * H + 7) / 8, 256, 0, s>>>(c.q, h->big, c.o, n * H, H, f16 != 0, T);
-  VPF_LAUNCH_CHECK();
-  gather_cls_kernel<<<(n * (D / 4) + 255) / 256, 256, 0, s>>>(h->X, c.xc, n, D, T);
-  VPF_LAUNCH_CHECK();
+  VPF_CUDA(launch_pdl(pdl_for_rows((long long)n * T), cls_attention_kernel, dim3((n * H + 7) / 8), dim3(256), 0, s, c.q, h->big, c.o,
+                      n * H, H, f16 != 0, T));
+  VPF_CUDA(launch_pdl(pdl_for_rows((long long)n * T), gather_cls_kernel, dim3((n * (D / 4) + 255) / 256), dim3(256), 0, s, h->X, c.xc,
+                      n, D, T));
   {
     GemmArgs g{n, D, D, w.proj_b, c.xc, nullptr};
       g.f16 = f16;
     if ((rc = launch_gemm(h->a_ocls, w.m_proj, g, kBiasResidualF32, s))) return rc;
   }
-  layernorm_kernel<__nv_bfloat16><<<(n + 7) / 8, 256, 0, s>>>(c.xc, D, w.ln2_g, w.ln2_b, c.xn, n, D, f16 != 0);
-  VPF_LAUNCH_CHECK();
+  VPF_CUDA(launch_layernorm<__nv_bfloat16>((n + 7) / 8, s, c.xc, D, w.ln2_g, w.ln2_b, c.xn, n, D, f16 != 0));
   {
     GemmArgs g{n, 4 * D, D, w.fc1_b, c.hc, nullptr};
       g.f16 = f16;
@@ -670,8 +693,7 @@ static int run_last_block_cls(vpf_vit* h, const LayerW& w, int n, float* emb, cu
       g.f16 = f16;
     if ((rc = launch_gemm(h->a_hc, w.m_fc2, g, kBiasResidualF32, s))) return rc;
   }
-  layernorm_kernel<float><<<(n + 7) / 8, 256, 0, s>>>(c.xc, D, h->norm_g, h->norm_b, emb, n, D);
-  VPF_LAUNCH_CHECK();
+  VPF_CUDA(launch_layernorm<float>((n + 7) / 8, s, c.xc, D, h->norm_g, h->norm_b, emb, n, D));
   return VPF_OK;
 }
 
@@ -704,8 +726,8 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
     h->maps_patches = patches;
   }
 
-  cls_init_kernel<<<(n * D + 255) / 256, 256, 0, s>>>(h->X, h->cls, h->pos, n, D, T);
-  VPF_LAUNCH_CHECK();
+  VPF_CUDA(launch_pdl(pdl_for_rows((long long)n * T), cls_init_kernel, dim3((n * D + 255) / 256), dim3(256), 0, s, h->X, h->cls,
+                      h->pos, n, D, T));
   {
     GemmArgs g{M0, D, 768, h->patch_b, h->X, h->pos};
     g.f16 = h->cfg.dtype == VPF_DTYPE_F16;
@@ -716,9 +738,7 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
   for (int l = 0; l < full_blocks; ++l)
     if ((rc = run_block(h, h->layers[l], n, s))) return rc;
   if (h->cls_prune) return run_last_block_cls(h, h->layers[L - 1], n, emb, s);
-  layernorm_kernel<float><<<(n + 7) / 8, 256, 0, s>>>(h->X, (size_t)T * D, h->norm_g,
-                                                     h->norm_b, emb, n, D);
-  VPF_LAUNCH_CHECK();
+  VPF_CUDA(launch_layernorm<float>((n + 7) / 8, s, h->X, (size_t)T * D, h->norm_g, h->norm_b, emb, n, D));
   return VPF_OK;
 }
 
@@ -744,9 +764,7 @@ int vpf_layernorm(const float* x, const float* gamma, const float* beta, void* o
                   int D, void* stream) {
   VPF_REQUIRE(x && gamma && beta && out_bf16 && rows > 0 && D > 0 && D % 4 == 0 && D <= 1024,
               "vpf_layernorm: bad arguments (D multiple of 4, <= 1024)");
-  layernorm_kernel<__nv_bfloat16><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-      x, D, gamma, beta, (__nv_bfloat16*)out_bf16, rows, D);
-  VPF_LAUNCH_CHECK();
+  VPF_CUDA(launch_layernorm<__nv_bfloat16>((rows + 7) / 8, (cudaStream_t)stream, x, D, gamma, beta, (__nv_bfloat16*)out_bf16, rows, D));
   return VPF_OK;
 }
 
