@@ -133,3 +133,22 @@ def test_frame_ingest_prefetch_matches_direct_stepping():
     with pytest.raises(ValueError):
         ingest.submit(np.zeros((10, 10, 3), np.uint8))
     assert list(track(b, [], ingest)) == []
+
+
+def test_frame_layouts_numpy_views_and_cuda_tensors_agree():
+    """A negatively-strided numpy view (OpenCV's BGR->RGB flip), a CPU tensor and a CUDA tensor of
+    the same pixels must give the same step."""
+    from vitparticlefiltertracker_b200 import Tracker
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+    dev = cuda()
+    frames, gt = make_clip("box", 120, 160, 3, seed=6, target=(32, 24))
+    bgr = np.ascontiguousarray(frames[..., ::-1])
+    res = []
+    for kind in ("numpy_view", "cpu_tensor", "cuda_tensor"):
+        trk = Tracker("vit_tiny_patch16_224", 64, seed=2)
+        conv = {"numpy_view": lambda f: bgr[f][..., ::-1],
+                "cpu_tensor": lambda f: torch.from_numpy(frames[f]),
+                "cuda_tensor": lambda f: torch.from_numpy(frames[f]).to(dev)}[kind]
+        trk.init(conv(0), gt[0])
+        res.append([trk.step(conv(f)) for f in (1, 2)])
+    assert res[0] == res[1] == res[2]

@@ -101,7 +101,8 @@ class Tracker:
     # -- helpers -----------------------------------------------------------------------------
     def _to_device_frame(self, frame):
         if isinstance(frame, np.ndarray):
-            frame = torch.from_numpy(frame)
+            # e.g. an OpenCV BGR->RGB view (frame[..., ::-1]) has negative strides
+            frame = torch.from_numpy(np.ascontiguousarray(frame))
         if frame.dtype != torch.uint8 or frame.dim() != 3 or frame.shape[2] != 3:
             raise ValueError("frame must be uint8 [H, W, 3] RGB")
         if not frame.is_cuda:
