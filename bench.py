@@ -161,10 +161,12 @@ def run_reference(args, emit):
     emit(line)
 
 
-def workload_config(n_gpus):
-    return {"workload": "BASELINE configs[2]: ViT-B/16 @224, 4096 particles per GPU, systematic "
+def workload_config(n_gpus, model=MODEL):
+    name = ("BASELINE configs[2]: ViT-B/16 @224" if model == MODEL else
+            f"BASELINE configs[3] shape ({model}; --model overrides the headline ViT-B/16)")
+    return {"workload": name + ", 4096 particles per GPU, systematic "
                         "resampling every frame, synthetic 1080p moving-target clip",
-            "model": MODEL, "particles_per_gpu": PARTICLES_PER_GPU,
+            "model": model, "particles_per_gpu": PARTICLES_PER_GPU,
             "particles_total": PARTICLES_PER_GPU * n_gpus, "frame": "1080x1920x3 uint8",
             "parallelism": f"particle-sharded x{n_gpus}",
             "l2": "per-step working set ~10 GB per GPU >> 126 MB L2 (inputs larger than L2)"}
@@ -342,6 +344,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default=MODEL,
+                    help="encoder (default: the headline ViT-B/16; vit_large_patch16_224 with "
+                         "--gpus 8 is BASELINE configs[3]: 32768 particles sharded over 8 GPUs)")
     ap.add_argument("--no-native", action="store_true",
                     help="skip the informative crop-size-64 operating point")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
@@ -386,7 +391,7 @@ def main():
     frames_host = torch.from_numpy(frames).pin_memory()
     frames_dev = torch.from_numpy(frames).to(dev)
     op_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
-    trk = Tracker(MODEL, n_total, seed=0, device=dev, process_group=pg, dtype=op_dtype)
+    trk = Tracker(args.model, n_total, seed=0, device=dev, process_group=pg, dtype=op_dtype)
     trk.init(frames_dev[0], gt[0])
 
     def barrier():
@@ -424,7 +429,7 @@ def main():
     hbm = hbm_kernels(dev, trk, frames_dev[1], peaks) if rank == 0 else None
     stages = stage_times(dev, trk, frames_dev[1]) if rank == 0 else None
     native = None
-    if n_gpus == 1 and not args.no_native:
+    if n_gpus == 1 and not args.no_native and args.model == MODEL:
         native = native_resolution_point(dev, frames_dev, frames_host, gt, op_dtype)
     barrier()
 
@@ -436,14 +441,14 @@ def main():
         ms_step = ms_dev / args.steps
         value = n_total * args.steps / (ms_dev / 1e3)
         e2e_v = n_total * args.steps / (ms_e2e / 1e3)
-        fl = flops_per_crop(MODEL)
-        roof["share_of_step"] = gemm_ms * 12 / ms_step     # upper bound: the last block is CLS-only
+        fl = flops_per_crop(args.model)
+        roof["share_of_step"] = gemm_ms * trk.encoder.depth / ms_step   # upper bound: the last block is CLS-only
         launches_per_step = trk.encoder.launches + 7      # + propagate, crop, loglik, max_reduce,
         line = {                                          #   sumexp, weights, resample
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": workload_config(n_gpus),
+            "config": workload_config(n_gpus, args.model),
             "frames_per_s": args.steps / (ms_dev / 1e3),
             "step_tflops_per_gpu": trk.n * fl / (ms_step / 1e3) / 1e12,
             "step_frac_of_sustained_peak": trk.n * fl / (ms_step / 1e3) / 1e12 / peaks["tflops_sustained"],
@@ -456,7 +461,7 @@ def main():
         }
         if native is not None:
             line["native_resolution"] = native
-        if n_gpus == 1 and not args.no_cpu_baseline:
+        if n_gpus == 1 and not args.no_cpu_baseline and args.model == MODEL:
             n_sample = 32
             v, sec, threads = cpu_oracle_run(2, 1, n_sample, frames[:4], gt[:4])
             line["cpu_baseline"] = {
