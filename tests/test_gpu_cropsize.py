@@ -119,7 +119,8 @@ def test_patch_embed_row_remap_small_grid():
 
 @pytest.mark.parametrize("model,n,S", [("vit_tiny_patch16_224", 9, 64), ("vit_tiny_patch16_224", 1, 16),
                                        ("vit_tiny_patch16_224", 5, 112), ("vit_tiny_patch16_224", 4, 128),
-                                       ("vit_base_patch16_224", 3, 64), ("vit_large_patch16_224", 2, 96)])
+                                       ("vit_base_patch16_224", 3, 64), ("vit_large_patch16_224", 2, 96),
+                                       ("vit_small_patch16_224", 4, 224), ("vit_small_patch16_224", 3, 80)])
 def test_vit_forward_small_crops_matches_oracle(model, n, S):
     from vitparticlefiltertracker_b200 import ops, pack_for_device
     dev = cuda()
