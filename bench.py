@@ -15,6 +15,8 @@ e2e    = the same through the public API with HOST frames: pinned host -> device
 roofline = the tcgen05 GEMM family (qkv/proj/fc1/fc2), timed live with CUDA events inside a
          sustained loop, against MEASURED_PEAKS.json's sustained bf16 figure.
 cpu_baseline = the CPU oracle (a port: the upstream repo is a README only) on a bounded sample.
+residual_fp16 = (N=1 only, informative) the headline workload with the encoder's residual stream
+         stored in fp16 instead of fp32 (Tracker(residual_dtype=torch.float16)).
 native_resolution = (N=1 only, informative, measured after everything above) the same workload
          at crop size 64 -- SURVEY.md section 8f-2 "native-resolution crops": 17 tokens per
          particle instead of 197, position embedding resampled, oracle revised to match
@@ -337,6 +339,29 @@ def native_resolution_point(dev, frames_dev, frames_host, gt, op_dtype, crop_siz
     return res
 
 
+def residual16_point(dev, frames_dev, gt, op_dtype, steps=8, warmup=3):
+    """The headline workload with the encoder's residual stream stored in fp16 (VPF_RESIDUAL_F16,
+    DESIGN.md section 6-0) instead of fp32: informative, not the headline."""
+    from vitparticlefiltertracker_b200 import Tracker
+    n = PARTICLES_PER_GPU
+    trk = Tracker(MODEL, n, seed=0, device=dev, dtype=op_dtype, residual_dtype=torch.float16)
+    trk.init(frames_dev[0], gt[0])
+    for i in range(warmup):
+        trk.step(frames_dev[1 + i % (CLIP_FRAMES - 1)])
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(steps):
+        trk.step(frames_dev[1 + (warmup + i) % (CLIP_FRAMES - 1)])
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    return {"ms_per_step": ms, "frames_per_s": 1e3 / ms, "particle_updates_per_s": n * 1e3 / ms,
+            "steps": steps,
+            "note": "informative operating point, not the headline: fp16 residual stream (half the "
+                    "residual bytes, +2 % distance to the fp32 oracle; tests/test_gpu_residual16.py)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -428,9 +453,10 @@ def main():
     roof, gemm_ms = gemm_roofline(dev, trk.n * 197, trk.dim, peaks) if rank == 0 else (None, 0.0)
     hbm = hbm_kernels(dev, trk, frames_dev[1], peaks) if rank == 0 else None
     stages = stage_times(dev, trk, frames_dev[1]) if rank == 0 else None
-    native = None
+    native, res16 = None, None
     if n_gpus == 1 and not args.no_native and args.model == MODEL:
         native = native_resolution_point(dev, frames_dev, frames_host, gt, op_dtype)
+        res16 = residual16_point(dev, frames_dev, gt, op_dtype)
     barrier()
 
     tracking = {"mean_iou_vs_ground_truth": float(np.mean(ious[: args.warmup + args.steps])),
@@ -461,6 +487,7 @@ def main():
         }
         if native is not None:
             line["native_resolution"] = native
+            line["residual_fp16"] = res16
         if n_gpus == 1 and not args.no_cpu_baseline and args.model == MODEL:
             n_sample = 32
             v, sec, threads = cpu_oracle_run(2, 1, n_sample, frames[:4], gt[:4])

@@ -32,11 +32,16 @@
 extern "C" {
 #endif
 
-#define VPF_ABI_VERSION 3
+#define VPF_ABI_VERSION 4
 
 /* 16-bit operand type of crops / ViT activations / weights (fp32 accumulation either way) */
 #define VPF_DTYPE_BF16 0
 #define VPF_DTYPE_F16 1
+/* storage type of the encoder's residual stream X [n*T][D]: fp32 (default, what the parity
+ * figures are quoted on) or fp16 with saturating conversion (half the residual bytes: X is 35 %
+ * of a block's HBM traffic; adds ~1e-3 relative error, |x| must stay below 65504) */
+#define VPF_RESIDUAL_F32 0
+#define VPF_RESIDUAL_F16 1
 
 typedef enum {
   VPF_OK = 0,
@@ -57,6 +62,7 @@ typedef struct {
   int32_t crop_size; /* S: input crop size in pixels, 0 or 224 = the default; a smaller multiple
                         of 16 gives P = (S/16)^2 patches and T = P + 1 tokens per crop (SURVEY.md
                         section 8f-2 "native-resolution crops"; oracle/vit.py resamples pos_embed) */
+  int32_t residual_dtype; /* VPF_RESIDUAL_F32 (default) or VPF_RESIDUAL_F16 */
 } vpf_vit_config;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -114,9 +120,11 @@ int vpf_vit_set_workspace(vpf_vit* h, void* workspace, size_t bytes);
 int vpf_vit_forward(vpf_vit* h, const void* patches_bf16, int n_crops, float* emb, void* stream);
 /* test hooks for single stages: C[M][N] = A[M][K] * W[N][K]^T (+ epilogue `mode`), LayerNorm,
  * attention.  mode: 0 bias->bf16, 1 bias+GELU->bf16, 2 bias+residual f32 in place,
- * 3 patch-embed (bias + pos, row remap into the (patches_per_crop + 1)-token stream, f32).     */
+ * 3 patch-embed (bias + pos, row remap into the (patches_per_crop + 1)-token stream, f32).
+ * residual_dtype (modes 2, 3): VPF_RESIDUAL_F32, or VPF_RESIDUAL_F16 when `out` is an fp16 stream. */
 int vpf_gemm_bf16(const void* A, const void* W, const float* bias, void* out, const float* pos,
-                  int M, int N, int K, int mode, int patches_per_crop, void* stream);
+                  int M, int N, int K, int mode, int patches_per_crop, int residual_dtype,
+                  void* stream);
 int vpf_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16,
                   int rows, int D, void* stream);
 /* qkv: bf16 [n_crops*tokens][3*64*heads], out: bf16 [n_crops*tokens][64*heads]; 2 <= tokens <= 197 */

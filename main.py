@@ -38,7 +38,9 @@ def main(path="config.yaml"):
                   sigma_vel=cfg.get("sigma_vel"), sigma_scale=cfg.get("sigma_scale", 0.01),
                   sigma_init=cfg.get("sigma_init"), state_dict=sd, dtype=dtype,
                   cuda_graph=bool(cfg.get("cuda_graph", False)),
-                  crop_size=int(cfg.get("crop_size", 224)))
+                  crop_size=int(cfg.get("crop_size", 224)),
+                  residual_dtype=torch.float16 if cfg.get("residual_dtype", "fp32") == "fp16"
+                  else torch.float32)
     trk.init(np.ascontiguousarray(frames[0]), bbox)
     for f in range(1, len(frames)):
         t0 = time.perf_counter()

@@ -309,7 +309,7 @@ def test_no_out_of_bounds_writes_with_canaries():
     n_el = ncrop * (P + 1) * D
     a, X = arena(n_el, torch.float32, 55.0)
     _lib.check(lib.vpf_gemm_bf16(A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), X.data_ptr(),
-                                 pos.data_ptr(), ncrop * P, D, 768, 3, P, stream), "vpf_gemm_bf16")
+                                 pos.data_ptr(), ncrop * P, D, 768, 3, P, 0, stream), "vpf_gemm_bf16")
     torch.cuda.synchronize()
     assert intact(a, n_el, 55.0)
     assert bool((X.view(ncrop, P + 1, D)[:, 0] == 55.0).all())     # CLS rows are not the GEMM's

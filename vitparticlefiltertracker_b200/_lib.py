@@ -13,11 +13,13 @@ _u64, _u32, _size_t = C.c_uint64, C.c_uint32, C.c_size_t
 
 class VitConfig(C.Structure):
     _fields_ = [("dim", C.c_int32), ("depth", C.c_int32), ("heads", C.c_int32),
-                ("max_crops", C.c_int32), ("dtype", C.c_int32), ("crop_size", C.c_int32)]
+                ("max_crops", C.c_int32), ("dtype", C.c_int32), ("crop_size", C.c_int32),
+                ("residual_dtype", C.c_int32)]
 
 
 DTYPE_BF16, DTYPE_F16 = 0, 1
-ABI_VERSION = 3          # VPF_ABI_VERSION in include/vpf.h
+RESIDUAL_F32, RESIDUAL_F16 = 0, 1
+ABI_VERSION = 4          # VPF_ABI_VERSION in include/vpf.h
 
 
 # name -> (restype, argtypes); mirrors include/vpf.h one to one
@@ -47,7 +49,7 @@ SIGNATURES = {
     "vpf_vit_set_workspace": (_c_int, [_c_void_p, _c_void_p, _size_t]),
     "vpf_vit_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p]),
     "vpf_gemm_bf16": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
-                               _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+                               _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "vpf_layernorm": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                                _c_void_p]),
     "vpf_attention": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),

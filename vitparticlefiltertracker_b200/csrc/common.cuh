@@ -102,6 +102,17 @@ __device__ __forceinline__ uint16_t pack16(float a, bool f16) {
   return *reinterpret_cast<uint16_t*>(&h);
 }
 
+// ---- 16-bit (fp16) residual stream option: saturating conversions ------------------------------
+// two floats -> packed fp16x2 (first element in the low half), overflow clamps to +-65504
+__device__ __forceinline__ uint32_t pack_h2_sat(float first, float second) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first));
+  return d;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+
 // ---- Philox4x32-10 (Random123 constants), shared by host and device ----------------------
 struct Philox4 {
   uint32_t v[4];

@@ -38,6 +38,7 @@ struct GemmArgs {
   const float* pos;
   int f16 = 0;   // 16-bit operand / output type: 0 = bf16, 1 = fp16
   int ppc = 196; // patch-embed mode: patches per crop (196 at crop size 224); tokens = ppc + 1
+  int x16 = 0;   // residual modes: the residual stream X is fp16 (saturating) instead of fp32
 };
 
 static constexpr int kBlockM = 128;
@@ -185,10 +186,13 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
       *reinterpret_cast<float4*>(slab + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
     }
     __syncwarp();
-    float* X = reinterpret_cast<float*>(g.out);
+    // X element (row, col + 4 p .. +3): fp32 -> 16 bytes, fp16 residual stream -> 8 bytes
+    const bool x16 = g.x16 != 0;
+    uint8_t* X = reinterpret_cast<uint8_t*>(g.out);
+    const size_t esz = x16 ? 2 : 4;
     const int p = lane & 7;
     float4 res[8];
-    float4* dst[8];
+    uint8_t* dst[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {           // all global loads first: 8 independent requests
       const int r = i * 4 + (lane >> 3);
@@ -197,11 +201,17 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
       if (grow < g.M) {
         if (MODE == kPatchEmbedF32) {
           const int crop = grow / g.ppc, pp = grow - crop * g.ppc;
-          dst[i] = reinterpret_cast<float4*>(X + ((size_t)crop * (g.ppc + 1) + 1 + pp) * g.N + col) + p;
+          dst[i] = X + ((((size_t)crop * (g.ppc + 1) + 1 + pp) * g.N + col) + 4 * p) * esz;
           res[i] = __ldg(reinterpret_cast<const float4*>(g.pos + (size_t)(1 + pp) * g.N + col) + p);
         } else {
-          dst[i] = reinterpret_cast<float4*>(X + (size_t)grow * g.N + col) + p;
-          res[i] = *dst[i];
+          dst[i] = X + (((size_t)grow * g.N + col) + 4 * p) * esz;
+          if (x16) {
+            const uint2 h = *reinterpret_cast<const uint2*>(dst[i]);
+            const float2 lo = unpack_h2(h.x), hi = unpack_h2(h.y);
+            res[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+          } else {
+            res[i] = *reinterpret_cast<const float4*>(dst[i]);
+          }
         }
       }
     }
@@ -212,7 +222,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
       if (dst[i]) {
         float4 o;
         o.x = a.x + res[i].x; o.y = a.y + res[i].y; o.z = a.z + res[i].z; o.w = a.w + res[i].w;
-        *dst[i] = o;
+        if (x16) *reinterpret_cast<uint2*>(dst[i]) = make_uint2(pack_h2_sat(o.x, o.y), pack_h2_sat(o.z, o.w));
+        else *reinterpret_cast<float4*>(dst[i]) = o;
       }
     }
   }
@@ -350,9 +361,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint8_t* xbuf = slabs + (warp - 2) * 8192;
       uint64_t* xbar = epi_bar + (warp - 2) * 2;
       uint32_t j = 0;
+      const bool x16 = g.x16 != 0;           // fp16 residual: 32 x 32 tile = 2 KB, 64-byte swizzle
       auto issue_load = [&](int tile_, int c_, uint32_t jj) {
         const int mb = tile_ / n_blocks, nb = tile_ - mb * n_blocks;
-        mbar_arrive_expect_tx(&xbar[jj & 1], 4096);
+        mbar_arrive_expect_tx(&xbar[jj & 1], x16 ? 2048u : 4096u);
         tma_load_2d(xbuf + (jj & 1) * 4096, &tmC, &xbar[jj & 1],
                     nb * BLOCK_N + half * kHalfCols + c_ * 32,
                     (mb * CTAS + (int)cta_rank) * kBlockM + quarter * 32);
@@ -383,18 +395,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tmem_ld_wait();
           const int col = n_blk * BLOCK_N + half * kHalfCols + c * 32;
           const float4* b4 = reinterpret_cast<const float4*>(g.bias + col);
-          uint8_t* buf = xbuf + (j & 1) * 4096 + lane * 128;
           mbar_wait(&xbar[j & 1], (j >> 1) & 1, 4);
+          if (x16) {
+            // row = 64 B: 16-byte piece q (8 halves) at lane*64 + ((q ^ ((lane>>1)&3)) << 4)
+            uint8_t* buf = xbuf + (j & 1) * 4096 + lane * 64;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4* px = reinterpret_cast<float4*>(buf + ((q ^ (lane & 7)) << 4));
-            const float4 b = __ldg(b4 + q);
-            float4 x = *px;
-            x.x += __uint_as_float(v[q * 4 + 0]) + b.x;
-            x.y += __uint_as_float(v[q * 4 + 1]) + b.y;
-            x.z += __uint_as_float(v[q * 4 + 2]) + b.z;
-            x.w += __uint_as_float(v[q * 4 + 3]) + b.w;
-            *px = x;
+            for (int q = 0; q < 4; ++q) {
+              uint4* px = reinterpret_cast<uint4*>(buf + ((q ^ ((lane >> 1) & 3)) << 4));
+              const float4 b0 = __ldg(b4 + 2 * q), b1 = __ldg(b4 + 2 * q + 1);
+              uint4 h = *px;
+              float2 x0 = unpack_h2(h.x), x1 = unpack_h2(h.y), x2 = unpack_h2(h.z), x3 = unpack_h2(h.w);
+              h.x = pack_h2_sat(x0.x + (__uint_as_float(v[q * 8 + 0]) + b0.x),
+                                x0.y + (__uint_as_float(v[q * 8 + 1]) + b0.y));
+              h.y = pack_h2_sat(x1.x + (__uint_as_float(v[q * 8 + 2]) + b0.z),
+                                x1.y + (__uint_as_float(v[q * 8 + 3]) + b0.w));
+              h.z = pack_h2_sat(x2.x + (__uint_as_float(v[q * 8 + 4]) + b1.x),
+                                x2.y + (__uint_as_float(v[q * 8 + 5]) + b1.y));
+              h.w = pack_h2_sat(x3.x + (__uint_as_float(v[q * 8 + 6]) + b1.z),
+                                x3.y + (__uint_as_float(v[q * 8 + 7]) + b1.w));
+              *px = h;
+            }
+          } else {
+            uint8_t* buf = xbuf + (j & 1) * 4096 + lane * 128;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4* px = reinterpret_cast<float4*>(buf + ((q ^ (lane & 7)) << 4));
+              const float4 b = __ldg(b4 + q);
+              float4 x = *px;
+              x.x += __uint_as_float(v[q * 4 + 0]) + b.x;
+              x.y += __uint_as_float(v[q * 4 + 1]) + b.y;
+              x.z += __uint_as_float(v[q * 4 + 2]) + b.z;
+              x.w += __uint_as_float(v[q * 4 + 3]) + b.w;
+              *px = x;
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();

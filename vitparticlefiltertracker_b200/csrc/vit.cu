@@ -184,7 +184,8 @@ static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   cfg.numAttrs = 2;
   CUtensorMap tmC = tmA;                       // modes 2 / 3 do not use it
   if (MODE <= 1 || MODE == kBiasResidualF32Tma) {
-    int rc = make_store_map(&tmC, g.out, (uint64_t)g.M, (uint64_t)g.N, MODE == kBiasResidualF32Tma);
+    int rc = make_store_map(&tmC, g.out, (uint64_t)g.M, (uint64_t)g.N,
+                            MODE == kBiasResidualF32Tma && !g.x16);
     if (rc) return rc;
   }
   VPF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g));
@@ -234,13 +235,16 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta,
                                                          OutT* __restrict__ out, int rows, int D,
-                                                         bool f16 = false) {
+                                                         bool f16 = false, bool x16 = false) {
   pdl_launch_dependents();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int nvec = D >> 2;
+  // x16: the residual stream is fp16 (`x` then points at halves; row_stride still in elements)
   const float4* x4 = reinterpret_cast<const float4*>(x + (size_t)row * row_stride);
+  const uint2* h4 = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(x) +
+                                                   (size_t)row * row_stride);
   pdl_wait();
   float4 v[8];
   float sum = 0.f;
@@ -248,7 +252,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   for (int i = 0; i < 8; ++i) {
     const int idx = lane + 32 * i;
     if (idx < nvec) {
-      v[i] = x4[idx];
+      if (x16) {
+        const uint2 h = h4[idx];
+        const float2 lo = unpack_h2(h.x), hi = unpack_h2(h.y);
+        v[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        v[i] = x4[idx];
+      }
       sum += v[i].x + v[i].y + v[i].z + v[i].w;
     }
   }
@@ -289,20 +299,22 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 template <typename OutT>
 static cudaError_t launch_layernorm(int blocks, cudaStream_t s, const float* x, size_t row_stride,
                                     const float* gamma, const float* beta, OutT* out, int rows,
-                                    int D, bool f16 = false) {
+                                    int D, bool f16 = false, bool x16 = false) {
   return launch_pdl(pdl_for_rows(rows), layernorm_kernel<OutT>, dim3(blocks), dim3(256), 0, s, x, row_stride, gamma, beta,
-                    out, rows, D, f16);
+                    out, rows, D, f16, x16);
 }
 
 // X[crop*T][:] = cls + pos[0]
 __global__ void cls_init_kernel(float* __restrict__ X, const float* __restrict__ cls,
-                                const float* __restrict__ pos, int n_crops, int D, int T) {
+                                const float* __restrict__ pos, int n_crops, int D, int T, bool x16) {
   pdl_launch_dependents();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_crops * D) return;
   pdl_wait();       // X is still read by the previous forward's last kernels
   int crop = i / D, d = i - crop * D;
-  X[(size_t)crop * T * D + d] = cls[d] + pos[d];
+  const float v = cls[d] + pos[d];
+  if (x16) reinterpret_cast<__half*>(X)[(size_t)crop * T * D + d] = __float2half_rn(v);
+  else X[(size_t)crop * T * D + d] = v;
 }
 
 // VPF_ATTN=mma selects the warp-level mma.sync kernel; default is the tcgen05 kernel.
@@ -362,15 +374,22 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_
 // token's output depends on the other tokens only through their keys and values) --------------
 // Xc[crop][:] = X[crop*197][:]
 __global__ void gather_cls_kernel(const float* __restrict__ X, float* __restrict__ Xc, int n_crops,
-                                  int D, int T) {
+                                  int D, int T, bool x16) {
   pdl_launch_dependents();
   int i = blockIdx.x * blockDim.x + threadIdx.x;     // float4 index
   const int nv = D >> 2;
   if (i >= n_crops * nv) return;
   pdl_wait();
   int crop = i / nv, v = i - crop * nv;
-  reinterpret_cast<float4*>(Xc)[i] =
-      reinterpret_cast<const float4*>(X + (size_t)crop * T * D)[v];
+  if (x16) {
+    const uint2 h = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(X) +
+                                                   (size_t)crop * T * D)[v];
+    const float2 lo = unpack_h2(h.x), hi = unpack_h2(h.y);
+    reinterpret_cast<float4*>(Xc)[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+  } else {
+    reinterpret_cast<float4*>(Xc)[i] =
+        reinterpret_cast<const float4*>(X + (size_t)crop * T * D)[v];
+  }
 }
 
 // One warp per (crop, head): o = softmax(q K^T / 8) V for the single CLS query.
@@ -468,6 +487,7 @@ using namespace vpf;
 
 struct vpf_vit {
   vpf_vit_config cfg;
+  bool x16 = false;             // residual stream X in fp16 (cfg.residual_dtype), else fp32
   int tokens = kMaxTokens;      // T = ppc + 1
   int ppc = kMaxTokens - 1;     // patches per crop = (crop_size / 16)^2
   bool has_weights = false, has_ws = false;
@@ -519,6 +539,8 @@ int vpf_vit_create(vpf_vit** out, const vpf_vit_config* cfg) {
               "vpf_vit_create: dtype must be VPF_DTYPE_BF16 or VPF_DTYPE_F16");
   VPF_REQUIRE(tokens_of(cfg) > 0, "vpf_vit_create: crop_size %d must be 0 (= 224) or a multiple of 16 in [16, 224]",
               cfg->crop_size);
+  VPF_REQUIRE(cfg->residual_dtype == VPF_RESIDUAL_F32 || cfg->residual_dtype == VPF_RESIDUAL_F16,
+              "vpf_vit_create: residual_dtype must be VPF_RESIDUAL_F32 or VPF_RESIDUAL_F16");
   if (!pick_block_n(cfg->dim) || !pick_block_n(3 * cfg->dim)) {
     set_error("vpf_vit_create: dim %d unsupported (dim and 3*dim must be multiples of 128)", cfg->dim);
     return VPF_ERR_UNSUPPORTED;
@@ -527,6 +549,7 @@ int vpf_vit_create(vpf_vit** out, const vpf_vit_config* cfg) {
   h->cfg = *cfg;
   h->tokens = tokens_of(cfg);
   h->ppc = h->tokens - 1;
+  h->x16 = cfg->residual_dtype == VPF_RESIDUAL_F16;
   h->layers.resize(cfg->depth);
   {
     const char* e = getenv("VPF_CLS_PRUNE");    // VPF_CLS_PRUNE=0: run the last block on all rows
@@ -544,7 +567,8 @@ int vpf_vit_destroy(vpf_vit* h) {
 size_t vpf_vit_workspace_bytes(const vpf_vit_config* cfg) {
   if (!cfg || !tokens_of(cfg)) return 0;
   const size_t rows = (size_t)cfg->max_crops * tokens_of(cfg), D = cfg->dim;
-  return align_up(rows * D * 4, 1024) + align_up(rows * D * 2, 1024) +
+  const size_t xsz = cfg->residual_dtype == VPF_RESIDUAL_F16 ? 2 : 4;
+  return align_up(rows * D * xsz, 1024) + align_up(rows * D * 2, 1024) +
          align_up(rows * 4 * D * 2, 1024) + cls_bytes(cfg->max_crops, D) + 1024;
 }
 
@@ -591,7 +615,7 @@ int vpf_vit_set_workspace(vpf_vit* h, void* ws, size_t bytes) {
               "vpf_vit_set_workspace: need %zu bytes, got %zu", vpf_vit_workspace_bytes(&h->cfg), bytes);
   const size_t rows = (size_t)h->cfg.max_crops * h->tokens, D = h->cfg.dim;
   uint8_t* b = (uint8_t*)ws;
-  h->X = (float*)b;            b += align_up(rows * D * 4, 1024);
+  h->X = (float*)b;            b += align_up(rows * D * (h->x16 ? 2 : 4), 1024);
   h->Xn = (__nv_bfloat16*)b;   b += align_up(rows * D * 2, 1024);
   h->big = (__nv_bfloat16*)b;  b += align_up(rows * 4 * D * 2, 1024);
   h->cbuf = b;
@@ -613,7 +637,7 @@ static int run_block(vpf_vit* h, const LayerW& w, int n, cudaStream_t s) {
   const int f16 = h->cfg.dtype == VPF_DTYPE_F16;
   const int ln_blocks = (M + 7) / 8;
   int rc;
-  VPF_CUDA(launch_layernorm<__nv_bfloat16>(ln_blocks, s, h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0));
+  VPF_CUDA(launch_layernorm<__nv_bfloat16>(ln_blocks, s, h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0, h->x16));
   {
     GemmArgs g{M, 3 * D, D, w.qkv_b, h->big, nullptr};
       g.f16 = f16;
@@ -623,9 +647,10 @@ static int run_block(vpf_vit* h, const LayerW& w, int n, cudaStream_t s) {
   {
     GemmArgs g{M, D, D, w.proj_b, h->X, nullptr};
       g.f16 = f16;
+      g.x16 = h->x16;
     if ((rc = launch_gemm(h->a_xn, w.m_proj, g, kBiasResidualF32, s))) return rc;
   }
-  VPF_CUDA(launch_layernorm<__nv_bfloat16>(ln_blocks, s, h->X, D, w.ln2_g, w.ln2_b, h->Xn, M, D, f16 != 0));
+  VPF_CUDA(launch_layernorm<__nv_bfloat16>(ln_blocks, s, h->X, D, w.ln2_g, w.ln2_b, h->Xn, M, D, f16 != 0, h->x16));
   {
     GemmArgs g{M, 4 * D, D, w.fc1_b, h->big, nullptr};
       g.f16 = f16;
@@ -634,6 +659,7 @@ static int run_block(vpf_vit* h, const LayerW& w, int n, cudaStream_t s) {
   {
     GemmArgs g{M, D, 4 * D, w.fc2_b, h->X, nullptr};
       g.f16 = f16;
+      g.x16 = h->x16;
     if ((rc = launch_gemm(h->a_big, w.m_fc2, g, kBiasResidualF32, s))) return rc;
   }
   return VPF_OK;
@@ -662,7 +688,7 @@ static int run_last_block_cls(vpf_vit* h, const LayerW& w, int n, float* emb, cu
   const int f16 = h->cfg.dtype == VPF_DTYPE_F16;
   const ClsBufs c = cls_bufs(h, n);
   int rc;
-  VPF_CUDA(launch_layernorm<__nv_bfloat16>((M + 7) / 8, s, h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0));
+  VPF_CUDA(launch_layernorm<__nv_bfloat16>((M + 7) / 8, s, h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0, h->x16));
   {  // K, V for every token: rows [D, 3D) of the fused qkv weight
     GemmArgs g{M, 2 * D, D, w.qkv_b + D, h->big, nullptr};
       g.f16 = f16;
@@ -676,7 +702,7 @@ static int run_last_block_cls(vpf_vit* h, const LayerW& w, int n, float* emb, cu
   VPF_CUDA(launch_pdl(pdl_for_rows((long long)n * T), cls_attention_kernel, dim3((n * H + 7) / 8), dim3(256), 0, s, c.q, h->big, c.o,
                       n * H, H, f16 != 0, T));
   VPF_CUDA(launch_pdl(pdl_for_rows((long long)n * T), gather_cls_kernel, dim3((n * (D / 4) + 255) / 256), dim3(256), 0, s, h->X, c.xc,
-                      n, D, T));
+                      n, D, T, h->x16));
   {
     GemmArgs g{n, D, D, w.proj_b, c.xc, nullptr};
       g.f16 = f16;
@@ -727,24 +753,26 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
   }
 
   VPF_CUDA(launch_pdl(pdl_for_rows((long long)n * T), cls_init_kernel, dim3((n * D + 255) / 256), dim3(256), 0, s, h->X, h->cls,
-                      h->pos, n, D, T));
+                      h->pos, n, D, T, h->x16));
   {
     GemmArgs g{M0, D, 768, h->patch_b, h->X, h->pos};
     g.f16 = h->cfg.dtype == VPF_DTYPE_F16;
     g.ppc = h->ppc;
+    g.x16 = h->x16;
     if ((rc = launch_gemm(h->a_patches, h->m_patch, g, kPatchEmbedF32, s))) return rc;
   }
   const int full_blocks = h->cls_prune ? L - 1 : L;
   for (int l = 0; l < full_blocks; ++l)
     if ((rc = run_block(h, h->layers[l], n, s))) return rc;
   if (h->cls_prune) return run_last_block_cls(h, h->layers[L - 1], n, emb, s);
-  VPF_CUDA(launch_layernorm<float>((n + 7) / 8, s, h->X, (size_t)T * D, h->norm_g, h->norm_b, emb, n, D));
+  VPF_CUDA(launch_layernorm<float>((n + 7) / 8, s, h->X, (size_t)T * D, h->norm_g, h->norm_b, emb, n, D, false, h->x16));
   return VPF_OK;
 }
 
 // ---- single-stage test hooks ----------------------------------------------------------------
 int vpf_gemm_bf16(const void* A, const void* W, const float* bias, void* out, const float* pos,
-                  int M, int N, int K, int mode, int patches_per_crop, void* stream) {
+                  int M, int N, int K, int mode, int patches_per_crop, int residual_dtype,
+                  void* stream) {
   VPF_REQUIRE(A && W && bias && out && M > 0 && N > 0 && K > 0, "vpf_gemm_bf16: bad arguments");
   VPF_REQUIRE(K % kBlockK == 0, "vpf_gemm_bf16: K=%d must be a multiple of 64", K);
   VPF_REQUIRE(mode != kPatchEmbedF32 || (pos && patches_per_crop > 0),
@@ -757,6 +785,7 @@ int vpf_gemm_bf16(const void* A, const void* W, const float* bias, void* out, co
   if ((rc = make_map(&mb, W, N, K, bn / gemm_ctas()))) return rc;
   GemmArgs g{M, N, K, bias, out, pos};
   if (mode == kPatchEmbedF32) g.ppc = patches_per_crop;
+  g.x16 = (mode >= kBiasResidualF32 && residual_dtype == VPF_RESIDUAL_F16) ? 1 : 0;
   return launch_gemm(ma, mb, g, mode, (cudaStream_t)stream);
 }
 

@@ -144,9 +144,12 @@ def gemm_bf16(a, w, bias, mode, out=None, pos=None, patches_per_crop=N_PATCH):
     if out is None:
         assert mode in (0, 1)
         out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    res16 = mode >= 2 and out.dtype == torch.float16        # fp16 residual stream (modes 2, 3)
     _lib.check(_lib.load().vpf_gemm_bf16(a.data_ptr(), w.data_ptr(), bias.data_ptr(),
                                          out.data_ptr(), _lib.ptr(pos), M, N, K, mode,
-                                         patches_per_crop, _stream()),
+                                         patches_per_crop,
+                                         _lib.RESIDUAL_F16 if res16 else _lib.RESIDUAL_F32,
+                                         _stream()),
                "vpf_gemm_bf16")
     return out
 
@@ -204,7 +207,7 @@ class VitEncoder:
     """Owns the opaque vpf_vit handle, the packed device weights and the workspace tensor."""
 
     def __init__(self, dim, depth, heads, max_crops, packed_weights, device="cuda",
-                 dtype=torch.bfloat16, crop_size=CROP):
+                 dtype=torch.bfloat16, crop_size=CROP, residual_dtype=torch.float32):
         lib = _lib.load()
         self._lib = lib
         self.dim, self.depth, self.heads, self.max_crops = dim, depth, heads, max_crops
@@ -218,7 +221,12 @@ class VitEncoder:
         wd = {t.dtype for t in packed_weights if t.dtype in (torch.bfloat16, torch.float16)}
         if wd != {dtype}:
             raise ValueError(f"packed GEMM weights are {wd}, encoder operand type is {dtype}")
-        self.cfg = _lib.VitConfig(dim, depth, heads, max_crops, _dtype_code(dtype), self.crop_size)
+        if residual_dtype not in (torch.float32, torch.float16):
+            raise ValueError("residual_dtype must be torch.float32 (default) or torch.float16")
+        self.residual_dtype = residual_dtype
+        self.cfg = _lib.VitConfig(dim, depth, heads, max_crops, _dtype_code(dtype), self.crop_size,
+                                  _lib.RESIDUAL_F16 if residual_dtype == torch.float16
+                                  else _lib.RESIDUAL_F32)
         self._h = C.c_void_p()
         _lib.check(lib.vpf_vit_create(C.byref(self._h), C.byref(self.cfg)), "vpf_vit_create")
         self.weights = [t.to(device).contiguous() for t in packed_weights]   # keep alive

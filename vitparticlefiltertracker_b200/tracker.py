@@ -38,7 +38,7 @@ class Tracker:
     def __init__(self, model="vit_base_patch16_224", n_particles=4096, seed=0, device="cuda",
                  dtype=torch.bfloat16, tau=0.1, sigma_pos=None, sigma_vel=None, sigma_scale=0.01,
                  sigma_init=None, state_dict=None, process_group=None, stream_id=0,
-                 encoder=None, cuda_graph=False, crop_size=224):
+                 encoder=None, cuda_graph=False, crop_size=224, residual_dtype=torch.float32):
         if not torch.cuda.is_available():
             raise RuntimeError("Tracker needs a CUDA device: the hot path has no CPU fallback")
         if dtype not in (torch.bfloat16, torch.float16):
@@ -71,7 +71,8 @@ class Tracker:
             sd = state_dict if state_dict is not None else init_state_dict(model)
             encoder = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], self.n,
                                      pack_for_device(model, sd, dtype, self.crop_size),
-                                     device=self.device, dtype=dtype, crop_size=self.crop_size)
+                                     device=self.device, dtype=dtype, crop_size=self.crop_size,
+                                     residual_dtype=residual_dtype)
         assert encoder.max_crops >= self.n and encoder.dtype == dtype
         assert encoder.crop_size == self.crop_size
         self.encoder = encoder
