@@ -225,6 +225,7 @@ def gemm_roofline(dev, M, D, peaks, reps=2):
                        f"{pj['gemm_family_algorithmic_bytes_per_block']:.4g}")
     return {"bound": "tensor", "kernel": "gemm_bf16_kernel<tcgen05, cta_group::2> (qkv+proj+fc1+fc2 of one block)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_burst": peaks["tflops_burst"], "frac_of_burst_peak": achieved / peaks["tflops_burst"],
             "peak_source": peaks["source"] + ", sustained bf16", "traffic": traffic,
             "traffic_source": traffic_src,
             "flops_per_launch_set": tot_fl, "ms_per_launch_set": tot_ms, "detail": detail}, tot_ms
