@@ -9,28 +9,30 @@ import json
 import sys
 import time
 
-import numpy as np
 import torch
 import yaml
 
-from vitparticlefiltertracker_b200 import Tracker
+from vitparticlefiltertracker_b200 import Tracker, track
+from vitparticlefiltertracker_b200.sources import array_frames, open_source
 from vitparticlefiltertracker_b200.synthetic import make_clip
 
 
 def main(path="config.yaml"):
     cfg = yaml.safe_load(open(path))
     inp = cfg.get("input", {})
-    if inp.get("kind", "synthetic") == "synthetic":
+    kind = inp.get("kind", "synthetic")
+    if kind == "synthetic":
         s = inp.get("synthetic", {})
-        frames, gt = make_clip(s.get("clip", "box"), s.get("height", 1080), s.get("width", 1920),
-                               s.get("frames", 16), s.get("seed", 0), tuple(s.get("target", (96, 96))),
-                               velocity=s.get("velocity"))
+        clip, gt = make_clip(s.get("clip", "box"), s.get("height", 1080), s.get("width", 1920),
+                             s.get("frames", 16), s.get("seed", 0), tuple(s.get("target", (96, 96))),
+                             velocity=s.get("velocity"))
+        frames = array_frames(clip)
         bbox = inp.get("bbox") or gt[0]
-    else:
-        frames = np.load(inp["path"], mmap_mode="r")
-        bbox = inp["bbox"]
+    else:                                   # npy | images | video (file or camera index)
+        frames = open_source(kind, inp["path"], max_frames=inp.get("max_frames"))
+        bbox = inp.get("bbox")
         if bbox is None:
-            raise SystemExit("input.bbox is required for npy input")
+            raise SystemExit(f"input.bbox (x, y, w, h of the target in the first frame) is required for {kind} input")
     sd = torch.load(cfg["checkpoint"], map_location="cpu") if cfg.get("checkpoint") else None
     dtype = torch.float16 if cfg.get("dtype", "bf16") == "fp16" else torch.bfloat16
     trk = Tracker(cfg.get("model", "vit_base_patch16_224"), cfg.get("n_particles", 4096),
@@ -41,13 +43,14 @@ def main(path="config.yaml"):
                   crop_size=int(cfg.get("crop_size", 224)),
                   residual_dtype=torch.float16 if cfg.get("residual_dtype", "fp32") == "fp16"
                   else torch.float32)
-    trk.init(np.ascontiguousarray(frames[0]), bbox)
-    for f in range(1, len(frames)):
-        t0 = time.perf_counter()
-        st = trk.step(np.ascontiguousarray(frames[f]))
+    frames = iter(frames)
+    trk.init(next(frames), bbox)
+    t0 = time.perf_counter()
+    for st in track(trk, frames):           # pinned double-buffered upload beside the tracking
+        t1 = time.perf_counter()
         print(json.dumps({"frame": st.frame_idx, "bbox": [round(v, 3) for v in st.bbox],
-                          "ess": round(st.ess, 2), "ms": round((time.perf_counter() - t0) * 1e3, 2)}),
-              flush=True)
+                          "ess": round(st.ess, 2), "ms": round((t1 - t0) * 1e3, 2)}), flush=True)
+        t0 = t1
 
 
 if __name__ == "__main__":

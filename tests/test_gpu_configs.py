@@ -157,3 +157,35 @@ def test_multistream_crop64_matches_single_stream_trackers():
             want = t.step(frames[f, s])
             assert torch.equal(mst.particles[s], t.particles), (f, s)
             assert np.allclose(got[s].bbox, want.bbox, atol=1e-9) and got[s].frame_idx == f
+
+
+def test_main_py_runs_synthetic_and_image_sequence_inputs(tmp_path):
+    """The README's `python main.py` usage (README.md:34-42) over the two kinds of input it names:
+    a (synthetic) video feed and images on disk; both must give the same track."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import yaml
+    cv2 = pytest.importorskip("cv2")
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+    cuda()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    syn = dict(clip="box", height=120, width=160, frames=5, target=[32, 24], seed=3)
+    base = dict(model="vit_tiny_patch16_224", n_particles=64, seed=1, crop_size=64, cuda_graph=False)
+    frames, gt = make_clip("box", 120, 160, 5, 3, (32, 24))
+    for i, fr in enumerate(frames):
+        cv2.imwrite(str(tmp_path / f"f{i:02d}.png"), fr[..., ::-1])
+    cfgs = {"syn": dict(base, input=dict(kind="synthetic", synthetic=syn)),
+            "img": dict(base, input=dict(kind="images", path=str(tmp_path / "f*.png"),
+                                         bbox=[float(v) for v in gt[0]]))}
+    out = {}
+    for name, cfg in cfgs.items():
+        p = tmp_path / f"{name}.yaml"
+        p.write_text(yaml.safe_dump(cfg))
+        r = subprocess.run([sys.executable, os.path.join(root, "main.py"), str(p)], capture_output=True,
+                           text=True, timeout=300, cwd=root)
+        assert r.returncode == 0, r.stderr[-1500:]
+        out[name] = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+        assert [o["frame"] for o in out[name]] == [1, 2, 3, 4]
+    assert [o["bbox"] for o in out["syn"]] == [o["bbox"] for o in out["img"]]
