@@ -18,6 +18,7 @@ sums), so the particle trajectory is bit-identical for any number of ranks.
 from __future__ import annotations
 
 import math
+import os
 from typing import NamedTuple
 
 import numpy as np
@@ -26,6 +27,24 @@ import torch
 from . import ops
 from .exchange import Exchange, shard_range
 from .vit_weights import VIT_CONFIGS, init_state_dict, pack_for_device
+
+
+class _Stage:
+    """NVTX range around one stage of a step (K1 crop, K2 ViT, K3 particle update, K4 resampling) so a
+    timeline lines up with SURVEY.md section 8a; active only when VPF_NVTX=1 (no cost otherwise)."""
+    enabled = os.environ.get("VPF_NVTX", "0") == "1"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Stage.enabled:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _Stage.enabled:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 class State(NamedTuple):
@@ -161,33 +180,38 @@ class Tracker:
         t = self.frame_idx
         st = self.particles
         # a3 motion
-        ops.propagate(st, self.sigma_pos, self.sigma_vel, self.sigma_scale, self.seed, t,
-                      self.stream_id, self.id_offset)
+        with _Stage("K3a propagate"):
+            ops.propagate(st, self.sigma_pos, self.sigma_vel, self.sigma_scale, self.seed, t,
+                          self.stream_id, self.id_offset)
         # a4 crop, a5 ViT
         if _emb is None:
-            ops.crop_state(frame, st, self.w0, self.h0, self.patches, crop_size=self.crop_size)
-            self.encoder.forward(self.patches, self.n, self.emb)
+            with _Stage("K1 crop"):
+                ops.crop_state(frame, st, self.w0, self.h0, self.patches, crop_size=self.crop_size)
+            with _Stage("K2 ViT encoder"):
+                self.encoder.forward(self.patches, self.n, self.emb)
             emb = self.emb
         else:
             emb = _emb
         # a6 likelihood + exact normalisation (collectives are no-ops on a single GPU)
         xch = self.xch
-        ops.loglik(emb, self.template, self.tau, self.logw, xch.max_local)
-        max_all = xch.gather_max()
-        ops.sumexp(self.logw, max_all, xch.sum_local)
-        sum_all = xch.gather_sum()
-        total, cdf, st_slot = xch.local_views()
-        self._stats.zero_()
-        ops.weights(self.logw, max_all, sum_all, st, self.weights, cdf, total, self._stats)
+        with _Stage("K3b weigh + normalise"):
+            ops.loglik(emb, self.template, self.tau, self.logw, xch.max_local)
+            max_all = xch.gather_max()
+            ops.sumexp(self.logw, max_all, xch.sum_local)
+            sum_all = xch.gather_sum()
+            total, cdf, st_slot = xch.local_views()
+            self._stats.zero_()
+            ops.weights(self.logw, max_all, sum_all, st, self.weights, cdf, total, self._stats)
         # a7 + a8 resample + gather
         u = ops.resample_uniform(self.seed, t, self.stream_id) if _u is None else float(_u)
-        if self.world > 1:
-            st_slot.copy_(st)
-            totals, cdf_all, state_all = xch.gather_records()
-            xch.reduce_stats(self._stats)
-        else:
-            totals, cdf_all, state_all = total, cdf, st
-        ops.resample(cdf_all, totals, self.n, self.id_offset, u, state_all, self._next, self.idx)
+        with _Stage("K4 resample + gather"):
+            if self.world > 1:
+                st_slot.copy_(st)
+                totals, cdf_all, state_all = xch.gather_records()
+                xch.reduce_stats(self._stats)
+            else:
+                totals, cdf_all, state_all = total, cdf, st
+            ops.resample(cdf_all, totals, self.n, self.id_offset, u, state_all, self._next, self.idx)
         self.particles, self._next = self._next, self.particles
         self.propagated = self._next            # pre-resampling state of this frame (tests)
         self.last_u = u
