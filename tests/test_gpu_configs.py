@@ -189,3 +189,26 @@ def test_main_py_runs_synthetic_and_image_sequence_inputs(tmp_path):
         out[name] = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
         assert [o["frame"] for o in out[name]] == [1, 2, 3, 4]
     assert [o["bbox"] for o in out["syn"]] == [o["bbox"] for o in out["img"]]
+
+
+def test_full_size_config5_share_matches_a_single_stream_tracker():
+    """BASELINE configs[4] per-GPU share at full size: 8 needle streams x 2048 particles, ViT-B/16,
+    one batched encoder call over 16 384 crops; stream 5 must follow an independent 2048-particle
+    Tracker bit for bit (batch invariance of every kernel at the largest single-GPU batch used)."""
+    from vitparticlefiltertracker_b200 import MultiStreamTracker, Tracker
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+    cuda()
+    S, n, model, probe = 8, 2048, "vit_base_patch16_224", 5
+    clips = [make_clip("needle", 480, 640, 3, seed=s, target=(3, 120), velocity=(1.5, 0.5)) for s in range(S)]
+    frames = np.stack([c[0] for c in clips], axis=1)                        # [F,S,H,W,3]
+    mst = MultiStreamTracker(S, model, n, seed=0)
+    mst.init(frames[0], [c[1][0] for c in clips])
+    one = Tracker(model, n, seed=0, stream_id=probe, encoder=None)
+    one.init(frames[0, probe], clips[probe][1][0])
+    for f in (1, 2):
+        states = mst.step(frames[f])
+        ref = one.step(frames[f, probe])
+        assert torch.equal(mst.particles[probe], one.particles), f
+        assert torch.equal(mst.idx[probe], one.idx)
+        assert np.allclose(states[probe].bbox, ref.bbox, atol=1e-9)
+        assert all(np.isfinite(st.bbox).all() and 1.0 <= st.ess <= n for st in states)
