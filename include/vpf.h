@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VPF_ABI_VERSION 4
+#define VPF_ABI_VERSION 5
 
 /* 16-bit operand type of crops / ViT activations / weights (fp32 accumulation either way) */
 #define VPF_DTYPE_BF16 0
@@ -135,19 +135,23 @@ int vpf_vit_launches(const vpf_vit* h);
 
 /* ---- a6: likelihood, normalisation, ESS, estimate (README.md:8; oracle/pf.py weigh, D9/D10) -
  * vpf_loglik:   logw[i] = cos(emb[i], tmpl) / tau;  local_max[0] = max_i logw[i].
- * vpf_sumexp:   m = max(rank_max[0..R)); local_sum[0] = sum_i snap36(expf(logw[i] - m)) (fp64,
+ * vpf_sumexp:   m = max(rank_max[0..R)); local_sum[0] = sum_i snap36(exp(logw[i] - m)) (fp64,
  *               exact -> independent of summation order and of R).
- * vpf_weights:  lse = float(m + log(sum_r rank_sum[r])); w[i] = expf(logw[i] - lse);
+ * vpf_weights:  lse = float(m + log(sum_r rank_sum[r])); w[i] = exp(logw[i] - lse);
  *               cdf_local[i] = inclusive fp64 scan of snap40(w) (exact), total_local[0] = last;
- *               stats[0..5) += (sum w, sum w^2, sum w*cx, sum w*cy, sum w*s) (fp64, caller
- *               zeroes `stats` first).                                                        */
+ *               stats[0..5) (+)= (sum w, sum w^2, sum w*cx, sum w*cy, sum w*s) in fp64:
+ *               accumulate != 0 adds to what is there (several shards into one vector, the
+ *               caller zeroes it first), accumulate == 0 overwrites.
+ * All exponentials are exp() in fp64 of an fp32 difference, rounded once to fp32, and the
+ * likelihood accumulates in fp64: given the embeddings, log-weights, weights
+ * and CDF equal the CPU oracle's bit for bit.  N_global <= 2^17 (exactness of the exp-sum).   */
 int vpf_loglik(const float* emb, int D, const float* tmpl, int n, float tau, float* logw,
                float* local_max, void* stream);
 int vpf_sumexp(const float* logw, int n, const float* rank_max, int R, double* local_sum,
                void* stream);
 int vpf_weights(const float* logw, int n, const float* rank_max, const double* rank_sum, int R,
                 const float* state, int ld, float* w, double* cdf_local, double* total_local,
-                double* stats, void* stream);
+                double* stats, int accumulate, void* stream);
 
 /* ---- a7 + a8: systematic resampling + state gather (README.md:8; oracle/pf.py, D6) ---------
  * Global CDF C[r*n_local + i] = sum_{r'<r} totals[r'] + cdf_all[r][i]  (exact in fp64).
@@ -162,6 +166,22 @@ int vpf_resample_dev(const double* cdf_all, const double* totals, int R, int n_l
                      uint32_t id_offset, uint64_t seed, uint32_t stream_id,
                      const uint32_t* frame_idx_dev, const float* state_all, float* state_out,
                      int ld_out, int32_t* idx, void* stream);
+
+
+/* Multi-GPU form: the R ranks' pieces are read in place from the
+ * all-gather's receive buffer.  Rank r's record starts at records + r*rec_stride (f64 slots):
+ *   [0] total   [1..6) stats (vpf_weights' five sums)   [6..8) unused
+ *   [8, 8+n_r) local inclusive CDF   [8+n_max, 8+4*n_max) state f32 [6][n_max] (ld = n_max)
+ * Shards may be uneven: shard_off (device, R+1 int32) holds each rank's first global particle id,
+ * shard_off[R] = N.  This rank resamples its n_local output slots [id_offset, id_offset+n_local).
+ * stats_out (optional, 5 f64) receives the sum over ranks of the records' stats, in rank order.
+ * frame_idx_dev != NULL: the uniform is derived on the device (CUDA-graph replay), `u` ignored. */
+#define VPF_RECORD_HEADER 8
+int vpf_resample_records(const double* records, long long rec_stride, int n_max,
+                         const int32_t* shard_off, int R, int n_local, uint32_t id_offset, double u,
+                         const uint32_t* frame_idx_dev, uint64_t seed, uint32_t stream_id,
+                         float* state_out, int ld_out, int32_t* idx, double* stats_out,
+                         void* stream);
 
 #ifdef __cplusplus
 }

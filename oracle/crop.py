@@ -26,7 +26,8 @@ PATCH_K = 3 * PATCH * PATCH   # 768
 
 def boxes_from_state(state: np.ndarray, w0: float, h0: float) -> np.ndarray:
     """[6,N] state -> [N,4] boxes (cx, cy, w, h) with w = w0*exp(s), h = h0*exp(s) (D5)."""
-    es = np.exp(state[4].astype(np.float32)).astype(np.float32)
+    # D14: exp evaluated in fp64, rounded once to fp32 (libm-independent, bit-equal on the GPU)
+    es = np.exp(state[4].astype(np.float32).astype(np.float64)).astype(np.float32)
     return np.stack([state[0], state[1], np.float32(w0) * es, np.float32(h0) * es],
                     axis=1).astype(np.float32)
 

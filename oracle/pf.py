@@ -18,8 +18,10 @@ CX, CY, VX, VY, S, SPARE = range(6)
 #: associative and the CDF does not depend on scan topology or rank count.
 GRID_BITS = 40
 #: exp(l_i - max) terms are snapped to multiples of 2^-SUM_GRID_BITS before the fp64 sum that
-#: feeds the log-sum-exp; N <= 2^15 terms <= 1 -> partial sums < 2^15 need 51 bits: exact.
+#: feeds the log-sum-exp; N <= 2^17 terms <= 1 -> every partial sum is an integer multiple of
+#: 2^-36 not above 2^17, i.e. fits the 53-bit significand: exact.  MAX_PARTICLES enforces it.
 SUM_GRID_BITS = 36
+MAX_PARTICLES = 1 << (53 - SUM_GRID_BITS)
 
 
 def init_particles(n: int, bbox, sigma_init: float, seed: int, stream_id: int = 0,
@@ -63,8 +65,9 @@ def weigh(emb: np.ndarray, tmpl: np.ndarray, tau: float, state: np.ndarray | Non
     """Cosine likelihood, log-sum-exp normalisation, ESS and weighted-mean estimate (D9, D10).
 
     emb [N, D] fp32, tmpl [D] fp32.  Returns dict(cos, logw, w, lse, ess, est) with w fp32 [N].
-    Dot products and norms accumulate in fp64 and are rounded once to fp32 (the GPU accumulates
-    in fp32 with a fixed tree -- compared with a tolerance, not bit-exactly).
+    Dot products and norms accumulate in fp64 and the cosine is rounded once to fp32; the GPU
+    does the same (fp64 accumulation, any order: the fp64 sums differ by ~1e-16 relative, which
+    the single rounding to fp32 absorbs), so log-weights agree bit for bit given the embeddings.
     """
     e = emb.astype(np.float64)
     t = tmpl.astype(np.float64)
@@ -80,15 +83,22 @@ def weigh(emb: np.ndarray, tmpl: np.ndarray, tau: float, state: np.ndarray | Non
     return out
 
 
+def exp_f32(x: np.ndarray) -> np.ndarray:
+    """fp32 -> fp32 exponential evaluated in fp64 and rounded once (D14): independent of the
+    libm that computes it, so CPU and GPU produce the same bits."""
+    return np.exp(np.asarray(x, dtype=np.float32).astype(np.float64)).astype(np.float32)
+
+
 def normalise(logw: np.ndarray) -> dict:
-    """m = max l; S = sum_fp64 snap36(exp_fp32(l - m)); lse = fp32(m + log S); w = exp_fp32(l - lse)."""
+    """m = max l; S = sum_fp64 snap36(exp(l - m)); lse = fp32(m + log S); w = exp(l - lse);
+    both exponentials are `exp_f32` of an fp32 difference (D14)."""
     logw = logw.astype(np.float32)
     m = np.float32(logw.max())
-    e = np.exp((logw - m).astype(np.float32)).astype(np.float32)
+    e = exp_f32((logw - m).astype(np.float32))
     snapped = np.rint(e.astype(np.float64) * 2.0 ** SUM_GRID_BITS) * 2.0 ** -SUM_GRID_BITS
     ssum = float(snapped.sum())
     lse = np.float32(np.float64(m) + np.log(ssum))
-    w = np.exp((logw - lse).astype(np.float32)).astype(np.float32)
+    w = exp_f32((logw - lse).astype(np.float32))
     ess = float(1.0 / np.sum(w.astype(np.float64) ** 2))
     return {"logw": logw, "w": w, "lse": lse, "max": m, "sumexp": ssum, "ess": ess}
 

@@ -53,16 +53,21 @@ def _split_seed(seed: int):
 
 
 def box_muller(ra, rb):
-    """Two uint32 arrays -> two fp32 standard normals (D7).
+    """Two uint32 arrays -> two fp32 standard normals (D7, revised by D14).
 
     u1 = ((ra >> 8) + 1) * 2^-24  in (0, 1]   (exactly representable in fp32)
     u2 =  (rb >> 8)      * 2^-24  in [0, 1)
-    z0 = sqrt(-2 ln u1) * cos(2 pi u2),  z1 = sqrt(-2 ln u1) * sin(2 pi u2), all in fp32.
+    z0 = fp32(sqrt(-2 ln u1) * cos(2 pi u2)),  z1 = fp32(sqrt(-2 ln u1) * sin(2 pi u2)).
+
+    D14: the transcendentals are evaluated in fp64 and the product is rounded ONCE to fp32.  An
+    fp64 libm result (error < 1-2 ulp of fp64) rounds to the same fp32 value whatever library
+    produced it (up to a ~2^-28 chance per value of straddling a rounding boundary), so the CPU
+    oracle and the GPU agree bit for bit instead of "to fp32 transcendental ulp".
     """
-    u1 = ((ra >> np.uint32(8)).astype(np.float32) + np.float32(1.0)) * np.float32(2.0 ** -24)
-    u2 = (rb >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
-    rad = np.sqrt(np.float32(-2.0) * np.log(u1)).astype(np.float32)
-    ang = (np.float32(2.0 * np.pi) * u2).astype(np.float32)
+    u1 = ((ra >> np.uint32(8)).astype(np.float64) + 1.0) * 2.0 ** -24
+    u2 = (rb >> np.uint32(8)).astype(np.float64) * 2.0 ** -24
+    rad = np.sqrt(-2.0 * np.log(u1))
+    ang = 6.283185307179586 * u2
     return (rad * np.cos(ang)).astype(np.float32), (rad * np.sin(ang)).astype(np.float32)
 
 

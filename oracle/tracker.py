@@ -31,6 +31,9 @@ class OracleTracker:
                  state_dict=None, stream_id=0, vit_chunk=32, crop_size=224):
         self.model = model
         self.n = int(n_particles)
+        if not 0 < self.n <= pf.MAX_PARTICLES:
+            raise ValueError(f"n_particles must be in [1, {pf.MAX_PARTICLES}]: the exact fp64 "
+                             "exp-sum (D10) needs log2(N) + 36 <= 53")
         self.seed = int(seed)
         self.tau = float(tau)
         self.stream_id = int(stream_id)

@@ -19,7 +19,7 @@ class VitConfig(C.Structure):
 
 DTYPE_BF16, DTYPE_F16 = 0, 1
 RESIDUAL_F32, RESIDUAL_F16 = 0, 1
-ABI_VERSION = 4          # VPF_ABI_VERSION in include/vpf.h
+ABI_VERSION = 5          # VPF_ABI_VERSION in include/vpf.h
 
 
 # name -> (restype, argtypes); mirrors include/vpf.h one to one
@@ -58,9 +58,12 @@ SIGNATURES = {
                             _c_void_p]),
     "vpf_sumexp": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p]),
     "vpf_weights": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int,
-                             _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+                             _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "vpf_resample": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _u32, _c_double, _c_void_p,
                               _c_void_p, _c_int, _c_void_p, _c_void_p]),
+    "vpf_resample_records": (_c_int, [_c_void_p, C.c_longlong, _c_int, _c_void_p, _c_int, _c_int,
+                                      _u32, _c_double, _c_void_p, _u64, _u32, _c_void_p, _c_int,
+                                      _c_void_p, _c_void_p, _c_void_p]),
 }
 
 _lib = None

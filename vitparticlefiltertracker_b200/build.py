@@ -5,6 +5,7 @@ driver-less machines (symbol / ABI tests), and the driver is only touched at run
 """
 from __future__ import annotations
 
+import fcntl
 import os
 import shutil
 import subprocess
@@ -38,8 +39,22 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles csrc/*.cu and links libvpf.so.  Safe under torchrun: ranks serialise on a file
+    lock (the first one builds, the others find the library up to date), and the library is
+    linked under a temporary name and renamed into place, so nobody dlopens a half-written file."""
     if not force and not needs_build():
         return LIB
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():      # another process built it while we waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
     procs = []
@@ -56,9 +71,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out.decode())
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
+    tmp = f"{LIB}.{os.getpid()}.tmp"
     cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-o", LIB, *objs]
+           "-o", tmp, *objs]
     subprocess.run(cmd, check=True)
+    os.replace(tmp, LIB)
     return LIB
 
 

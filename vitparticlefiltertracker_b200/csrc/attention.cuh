@@ -75,7 +75,9 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   const uint32_t sK = sQ + kQRows * 128;
   const uint32_t sV = sK + kKeyRows * 128;
   pdl_launch_dependents();
-  const int head = blockIdx.x, crop = blockIdx.y;
+  // (crop, head) flattened into grid.x: gridDim.y is capped at 65535, n_crops is not
+  const int heads_ = D / kHeadDim;
+  const int crop = blockIdx.x / heads_, head = blockIdx.x - crop * heads_;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t ld = (size_t)3 * D;
   pdl_wait();

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kV2Threads) crop_sep_kernel(const uint8_t* __r
   pdl_wait();                                                // the particle state is the motion kernel's output
   Box b;
   if (kFromState) {
-    float es = expf(src[4 * (size_t)ld + crop]);
+    const float es = (float)exp((double)src[4 * (size_t)ld + crop]);   // D14: fp64, rounded once
     b.cx = src[crop];
     b.cy = src[(size_t)ld + crop];
     b.w = __fmul_rn(w0, es);

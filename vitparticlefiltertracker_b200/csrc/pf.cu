@@ -17,15 +17,24 @@ static constexpr double kInvGrid40 = 1.0 / 1099511627776.0;  // 2^-40
 static constexpr double kGrid36 = 68719476736.0;             // 2^36
 static constexpr double kInvGrid36 = 1.0 / 68719476736.0;
 
-// ---- Box-Muller on 24-bit uniforms (oracle/philox.py box_muller) --------------------------
+// ---- Box-Muller on 24-bit uniforms (oracle/philox.py box_muller, D14) ------------------------
+// The transcendentals run in fp64 and the product is rounded once to fp32: an fp64 libm result
+// rounds to the same fp32 value whichever library produced it, so the normals -- and with them
+// the whole motion model -- equal the CPU oracle's bit for bit.  6 normals per particle per
+// frame: ~25 k fp64 transcendentals at N = 4096, nothing beside the encoder.
 __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float& z0, float& z1) {
-  float u1 = __fmul_rn(__fadd_rn((float)(ra >> 8), 1.0f), 5.9604644775390625e-08f);  // 2^-24
-  float u2 = __fmul_rn((float)(rb >> 8), 5.9604644775390625e-08f);
-  float rad = sqrtf(__fmul_rn(-2.0f, logf(u1)));
-  float ang = __fmul_rn(6.2831855f, u2);
-  z0 = __fmul_rn(rad, cosf(ang));
-  z1 = __fmul_rn(rad, sinf(ang));
+  const double u1 = ((double)(ra >> 8) + 1.0) * 5.9604644775390625e-08;  // 2^-24
+  const double u2 = (double)(rb >> 8) * 5.9604644775390625e-08;
+  const double rad = sqrt(-2.0 * log(u1));
+  const double ang = 6.283185307179586 * u2;
+  double sn, cs;
+  sincos(ang, &sn, &cs);
+  z0 = (float)(rad * cs);
+  z1 = (float)(rad * sn);
 }
+
+// fp32 -> fp32 exponential evaluated in fp64, rounded once (oracle/pf.py exp_f32, D14)
+__device__ __forceinline__ float exp_f32(float x) { return (float)exp((double)x); }
 
 __device__ __forceinline__ void six_normals(uint32_t id, uint32_t frame_idx, uint32_t stream_id,
                                             uint32_t k0, uint32_t k1, float z[6]) {
@@ -91,6 +100,9 @@ __global__ void propagate_kernel(float* __restrict__ st, int n, int ld, float sp
 }
 
 // ---- likelihood: one warp per particle -----------------------------------------------------
+// fp64 accumulation, one rounding to fp32 (oracle/pf.py weigh): fp64 sums in another order differ
+// by ~1e-16 relative, which the rounding absorbs, so log-weights equal the oracle's bit for bit
+// given the embeddings.  3 M fp64 FMAs at N = 4096, D = 768.
 __global__ void __launch_bounds__(256) loglik_kernel(const float* __restrict__ emb, int D,
                                                       const float* __restrict__ tmpl, int n,
                                                       float tau, float* __restrict__ logw) {
@@ -99,20 +111,21 @@ __global__ void __launch_bounds__(256) loglik_kernel(const float* __restrict__ e
   if (warp >= n) return;
   const float4* e4 = reinterpret_cast<const float4*>(emb + (size_t)warp * D);
   const float4* t4 = reinterpret_cast<const float4*>(tmpl);
-  float dot = 0.f, ne = 0.f, nt = 0.f;
+  double dot = 0.0, ne = 0.0, nt = 0.0;
   for (int i = lane; i < D / 4; i += 32) {
-    float4 e = e4[i];
-    float4 t = __ldg(t4 + i);
-    dot += e.x * t.x + e.y * t.y + e.z * t.z + e.w * t.w;
-    ne += e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
-    nt += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+    const float4 e = e4[i];
+    const float4 t = __ldg(t4 + i);
+    const double ex = e.x, ey = e.y, ez = e.z, ew = e.w, tx = t.x, ty = t.y, tz = t.z, tw = t.w;
+    dot += ex * tx + ey * ty + ez * tz + ew * tw;
+    ne += ex * ex + ey * ey + ez * ez + ew * ew;
+    nt += tx * tx + ty * ty + tz * tz + tw * tw;
   }
   dot = warp_sum(dot);
   ne = warp_sum(ne);
   nt = warp_sum(nt);
   if (lane == 0) {
-    float c = dot / (fmaxf(sqrtf(ne), 1e-8f) * fmaxf(sqrtf(nt), 1e-8f));
-    logw[warp] = c / tau;
+    const float c = (float)(dot / (fmax(sqrt(ne), 1e-8) * fmax(sqrt(nt), 1e-8)));
+    logw[warp] = __fdiv_rn(c, tau);
   }
 }
 
@@ -145,7 +158,7 @@ __global__ void __launch_bounds__(1024) sumexp_kernel(const float* __restrict__ 
   const float m = ranks_max(rank_max, R);
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float e = expf(__fsub_rn(logw[i], m));
+    float e = exp_f32(__fsub_rn(logw[i], m));
     acc += rint((double)e * kGrid36) * kInvGrid36;
   }
   acc = warp_sum(acc);
@@ -163,7 +176,7 @@ __global__ void __launch_bounds__(1024) weights_kernel(
     const float* __restrict__ logw, int n, const float* __restrict__ rank_max,
     const double* __restrict__ rank_sum, int R, const float* __restrict__ st, int ld,
     float* __restrict__ w_out, double* __restrict__ cdf, double* __restrict__ total,
-    double* __restrict__ stats) {
+    double* __restrict__ stats, int accumulate) {
   __shared__ double warp_tot[32];
   __shared__ double stat_sm[32][5];
   __shared__ double carry_sm;
@@ -179,7 +192,7 @@ __global__ void __launch_bounds__(1024) weights_kernel(
     int i = base + tid;
     double q = 0.0;
     if (i < n) {
-      float w = expf(__fsub_rn(logw[i], lse));
+      float w = exp_f32(__fsub_rn(logw[i], lse));
       w_out[i] = w;
       q = rint((double)w * kGrid40) * kInvGrid40;
       double wd = (double)w;
@@ -230,17 +243,34 @@ __global__ void __launch_bounds__(1024) weights_kernel(
   if (tid < 5) {
     double a = 0.0;
     for (int k = 0; k < 32; ++k) a += stat_sm[k][tid];
-    stats[tid] += a;
+    stats[tid] = accumulate ? stats[tid] + a : a;
   }
 }
 
 // ---- systematic resampling + gather --------------------------------------------------------
+// Where the R ranks' pieces of the global CDF / state live.  Two layouts feed the same kernel:
+//   separate arrays (single GPU, tests):  cdf f64 [R][n], totals f64 [R], state f32 [R][6][n];
+//   packed records (multi-GPU exchange):  rank r's record at rec + r*stride (f64 slots):
+//     [0] total  [1..6) stats  [8, 8+n_r) local inclusive CDF  [8+n_max, ...) state f32 [6][n_max]
+//   read in place from the all-gather's receive buffer -- no repacking kernels.
+// Shards may be uneven: shard_off[r] = first global particle id of rank r (device, R+1 ints);
+// nullptr = equal shards of n_equal.
+struct ResampleSrc {
+  const double* cdf;    long long cdf_stride;
+  const double* tot;    long long tot_stride;
+  const float* st;      long long st_stride;   int st_ld;
+  const int32_t* shard_off;                    int n_equal;
+  const double* stats;  long long stats_stride;  double* stats_out;   // optional rank reduction
+};
+
+static constexpr int kMaxRanks = 64;
+
 __global__ void __launch_bounds__(256) resample_kernel(
-    const double* __restrict__ cdf_all, const double* __restrict__ totals, int R, int n_local,
-    uint32_t id_offset, double u, const uint32_t* __restrict__ frame_idx_dev, uint32_t k0,
-    uint32_t k1, uint32_t stream_id, const float* __restrict__ state_all,
+    ResampleSrc src, int R, int n_local, uint32_t id_offset, double u,
+    const uint32_t* __restrict__ frame_idx_dev, uint32_t k0, uint32_t k1, uint32_t stream_id,
     float* __restrict__ state_out, int ld_out, int32_t* __restrict__ idx) {
-  extern __shared__ double offs[];  // [R] exclusive prefix of rank totals
+  __shared__ double offs[kMaxRanks + 1];   // exclusive prefix of rank totals; offs[R] = C_last
+  __shared__ int soff[kMaxRanks + 1];      // first global id of each rank; soff[R] = N
   if (frame_idx_dev) {              // CUDA-graph replay: derive the frame's uniform on device
     Philox4 r = philox4x32_10(0xFFFFFFFFu, *frame_idx_dev, stream_id, 2u, k0, k1);
     const uint64_t v = (((uint64_t)r.v[0] << 21) ^ ((uint64_t)r.v[1] >> 11)) & ((1ull << 53) - 1);
@@ -248,28 +278,41 @@ __global__ void __launch_bounds__(256) resample_kernel(
   }
   if (threadIdx.x == 0) {
     double a = 0.0;
-    for (int r = 0; r < R; ++r) { offs[r] = a; a = __dadd_rn(a, totals[r]); }
+    for (int r = 0; r < R; ++r) { offs[r] = a; a = __dadd_rn(a, src.tot[r * src.tot_stride]); }
+    offs[R] = a;                   // exact: every total is a multiple of 2^-40, the sum is < 2
   }
+  if (threadIdx.x <= R)
+    soff[threadIdx.x] = src.shard_off ? src.shard_off[threadIdx.x] : (int)threadIdx.x * src.n_equal;
   __syncthreads();
-  const int N = R * n_local;
-  const double c_last = __dadd_rn(offs[R - 1], cdf_all[(size_t)N - 1]);
-  const double step = __ddiv_rn(c_last, (double)N);
+  if (src.stats_out && blockIdx.x == 0 && threadIdx.x < 5) {
+    double a = 0.0;                // fixed rank order: every rank obtains the same estimate
+    for (int r = 0; r < R; ++r) a += src.stats[r * src.stats_stride + threadIdx.x];
+    src.stats_out[threadIdx.x] = a;
+  }
+  const int N = soff[R];
+  const double step = __ddiv_rn(offs[R], (double)N);
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_local) return;
   const double p = __dmul_rn(__dadd_rn((double)(id_offset + (uint32_t)j), u), step);
-  int lo = 0, hi = N;
+  // a = #{g : C[g] <= p}, C[g] = offs[r] + cdf_r[i] nondecreasing in g: every rank whose last
+  // value offs[r+1] is <= p counts in full; the first rank r with offs[r+1] > p is searched.
+  int r = 0;
+  while (r < R - 1 && offs[r + 1] <= p) ++r;
+  const double* c = src.cdf + r * src.cdf_stride;
+  const double base = offs[r];
+  int lo = 0, hi = soff[r + 1] - soff[r];
   while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    double c = __dadd_rn(offs[mid / n_local], cdf_all[mid]);
-    if (c <= p) lo = mid + 1; else hi = mid;
+    const int mid = (lo + hi) >> 1;
+    if (__dadd_rn(base, c[mid]) <= p) lo = mid + 1; else hi = mid;
   }
-  int a = lo < N - 1 ? lo : N - 1;
+  int a = soff[r] + lo;
+  if (a > N - 1) a = N - 1;
   idx[j] = a;
-  int r = a / n_local, i = a - r * n_local;
-  const float* src = state_all + (size_t)r * 6 * n_local + i;
+  const int i = a - soff[r];
+  const float* s = src.st + r * src.st_stride + i;
 #pragma unroll
   for (int row = 0; row < 6; ++row)
-    state_out[(size_t)row * ld_out + j] = src[(size_t)row * n_local];
+    state_out[(size_t)row * ld_out + j] = s[(size_t)row * src.st_ld];
 }
 
 static inline void split_seed(uint64_t seed, uint32_t& k0, uint32_t& k1) {
@@ -369,6 +412,11 @@ int vpf_loglik(const float* emb, int D, const float* tmpl, int n, float tau, flo
 int vpf_sumexp(const float* logw, int n, const float* rank_max, int R, double* local_sum,
                void* stream) {
   VPF_REQUIRE(logw && rank_max && local_sum && n > 0 && R > 0, "vpf_sumexp: bad arguments");
+  // terms <= 1 on a 2^-36 grid: the fp64 sum over all particles (of every rank) is exact, hence
+  // independent of order and of the number of ranks, only while log2(N_global) + 36 <= 53.  The
+  // caller owns the global count (Tracker checks it); the local count is checked here.
+  VPF_REQUIRE(n <= (1 << 17), "vpf_sumexp: %d particles exceed 2^17, the bound of the exact fp64 "
+              "exp-sum", n);
   sumexp_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logw, n, rank_max, R, local_sum);
   VPF_LAUNCH_CHECK();
   return VPF_OK;
@@ -376,26 +424,36 @@ int vpf_sumexp(const float* logw, int n, const float* rank_max, int R, double* l
 
 int vpf_weights(const float* logw, int n, const float* rank_max, const double* rank_sum, int R,
                 const float* state, int ld, float* w, double* cdf_local, double* total_local,
-                double* stats, void* stream) {
+                double* stats, int accumulate, void* stream) {
   VPF_REQUIRE(logw && rank_max && rank_sum && state && w && cdf_local && total_local && stats &&
                   n > 0 && R > 0 && ld >= n,
               "vpf_weights: bad arguments");
   weights_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logw, n, rank_max, rank_sum, R, state, ld,
-                                                       w, cdf_local, total_local, stats);
+                                                       w, cdf_local, total_local, stats, accumulate);
   VPF_LAUNCH_CHECK();
   return VPF_OK;
+}
+
+static ResampleSrc arrays_src(const double* cdf_all, const double* totals, const float* state_all,
+                              int n_local) {
+  ResampleSrc s = {};
+  s.cdf = cdf_all;  s.cdf_stride = n_local;
+  s.tot = totals;   s.tot_stride = 1;
+  s.st = state_all; s.st_stride = 6ll * n_local;  s.st_ld = n_local;
+  s.shard_off = nullptr;  s.n_equal = n_local;
+  return s;
 }
 
 int vpf_resample(const double* cdf_all, const double* totals, int R, int n_local,
                  uint32_t id_offset, double u, const float* state_all, float* state_out,
                  int ld_out, int32_t* idx, void* stream) {
-  VPF_REQUIRE(cdf_all && totals && state_all && state_out && idx && R > 0 && n_local > 0 &&
-                  ld_out >= n_local && u >= 0.0 && u < 1.0,
-              "vpf_resample: bad arguments (need 0 <= u < 1)");
+  VPF_REQUIRE(cdf_all && totals && state_all && state_out && idx && R > 0 && R <= kMaxRanks &&
+                  n_local > 0 && ld_out >= n_local && u >= 0.0 && u < 1.0,
+              "vpf_resample: bad arguments (need 0 <= u < 1, R <= 64)");
   VPF_REQUIRE((long long)R * n_local < (1ll << 31), "vpf_resample: too many particles");
-  resample_kernel<<<(n_local + 255) / 256, 256, R * sizeof(double), (cudaStream_t)stream>>>(
-      cdf_all, totals, R, n_local, id_offset, u, nullptr, 0u, 0u, 0u, state_all, state_out, ld_out,
-      idx);
+  resample_kernel<<<(n_local + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      arrays_src(cdf_all, totals, state_all, n_local), R, n_local, id_offset, u, nullptr, 0u, 0u,
+      0u, state_out, ld_out, idx);
   VPF_LAUNCH_CHECK();
   return VPF_OK;
 }
@@ -405,13 +463,37 @@ int vpf_resample_dev(const double* cdf_all, const double* totals, int R, int n_l
                      const uint32_t* frame_idx_dev, const float* state_all, float* state_out,
                      int ld_out, int32_t* idx, void* stream) {
   VPF_REQUIRE(cdf_all && totals && state_all && state_out && idx && frame_idx_dev && R > 0 &&
-                  n_local > 0 && ld_out >= n_local,
+                  R <= kMaxRanks && n_local > 0 && ld_out >= n_local,
               "vpf_resample_dev: bad arguments");
   VPF_REQUIRE((long long)R * n_local < (1ll << 31), "vpf_resample_dev: too many particles");
   uint32_t k0, k1; split_seed(seed, k0, k1);
-  resample_kernel<<<(n_local + 255) / 256, 256, R * sizeof(double), (cudaStream_t)stream>>>(
-      cdf_all, totals, R, n_local, id_offset, 0.0, frame_idx_dev, k0, k1, stream_id, state_all,
-      state_out, ld_out, idx);
+  resample_kernel<<<(n_local + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      arrays_src(cdf_all, totals, state_all, n_local), R, n_local, id_offset, 0.0, frame_idx_dev,
+      k0, k1, stream_id, state_out, ld_out, idx);
+  VPF_LAUNCH_CHECK();
+  return VPF_OK;
+}
+
+int vpf_resample_records(const double* records, long long rec_stride, int n_max,
+                         const int32_t* shard_off, int R, int n_local, uint32_t id_offset, double u,
+                         const uint32_t* frame_idx_dev, uint64_t seed, uint32_t stream_id,
+                         float* state_out, int ld_out, int32_t* idx, double* stats_out,
+                         void* stream) {
+  VPF_REQUIRE(records && shard_off && state_out && idx && R > 0 && R <= kMaxRanks && n_local > 0 &&
+                  n_max >= n_local && ld_out >= n_local &&
+                  rec_stride >= VPF_RECORD_HEADER + 4ll * n_max,
+              "vpf_resample_records: bad arguments (R <= 64, rec_stride >= 8 + 4 n_max)");
+  VPF_REQUIRE(frame_idx_dev || (u >= 0.0 && u < 1.0), "vpf_resample_records: need 0 <= u < 1");
+  ResampleSrc s = {};
+  s.cdf = records + VPF_RECORD_HEADER;  s.cdf_stride = rec_stride;
+  s.tot = records;                      s.tot_stride = rec_stride;
+  s.st = reinterpret_cast<const float*>(records + VPF_RECORD_HEADER + n_max);
+  s.st_stride = 2 * rec_stride;         s.st_ld = n_max;
+  s.shard_off = shard_off;              s.n_equal = 0;
+  s.stats = records + 1;                s.stats_stride = rec_stride;  s.stats_out = stats_out;
+  uint32_t k0, k1; split_seed(seed, k0, k1);
+  resample_kernel<<<(n_local + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      s, R, n_local, id_offset, u, frame_idx_dev, k0, k1, stream_id, state_out, ld_out, idx);
   VPF_LAUNCH_CHECK();
   return VPF_OK;
 }

@@ -134,16 +134,20 @@ static bool first_time_on_device(bool (&done)[32]) {
   return true;
 }
 
-static int g_num_sms = 0;
+// SM count of the CURRENT device (cached per device; a benign race: every writer stores the
+// same value).  CTA pairs need an even number of CTAs.
 static int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-    g_num_sms &= ~1;            // CTA pairs: an even number of CTAs
+  static int cache[32] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& v = cache[dev & 31];
+  if (!v) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    v = n & ~1;
   }
-  return g_num_sms;
+  return v;
 }
 
 // VPF_GEMM_CTAS=1 selects the single-CTA (cta_group::1) kernel; default is the CTA-pair kernel.
@@ -363,7 +367,7 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_
     if (first_time_on_device(attr))
       VPF_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kAttnSmem));
-    VPF_CUDA(launch_pdl(pdl_for_rows((long long)n_crops * tokens), attention_kernel, dim3(heads, n_crops), dim3(kAttnThreads),
+    VPF_CUDA(launch_pdl(pdl_for_rows((long long)n_crops * tokens), attention_kernel, dim3(heads * n_crops), dim3(kAttnThreads),
                         (size_t)kAttnSmem, s, qkv, out, D, tokens, f16 != 0));
   }
   VPF_LAUNCH_CHECK();

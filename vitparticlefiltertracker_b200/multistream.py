@@ -26,6 +26,8 @@ class MultiStreamTracker:
             raise RuntimeError("MultiStreamTracker needs a CUDA device: there is no CPU fallback")
         self.S, self.n, self.seed, self.tau = int(n_streams), int(n_particles), int(seed), float(tau)
         self.model, self.device = model, torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.crop_size = int(crop_size)
         self.n_patch = ops.n_patch(self.crop_size)
         self.sigma_scale = float(np.float32(sigma_scale))

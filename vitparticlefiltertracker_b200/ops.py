@@ -6,6 +6,7 @@ hand-written sm_100a kernels.  All calls enqueue on the current torch stream and
 from __future__ import annotations
 
 import ctypes as C
+import functools
 
 import torch
 
@@ -33,6 +34,23 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_device(fn):
+    """Runs `fn` with the CUDA device of its first CUDA-tensor argument current.  libvpf takes the
+    launch stream from `torch.cuda.current_stream()` and keys its per-device state on
+    `cudaGetDevice()`, so a tracker built on cuda:k must work while another device is current
+    (a single process driving several GPUs)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapper
+
+
 def _dtype_code(dtype) -> int:
     if dtype == torch.bfloat16:
         return _lib.DTYPE_BF16
@@ -46,36 +64,49 @@ def _dev(t: torch.Tensor, dtype) -> torch.Tensor:
     return t
 
 
+def _state(t: torch.Tensor) -> torch.Tensor:
+    """Particle state: fp32 SoA [6, n], unit stride along particles, any row pitch >= n (the
+    multi-GPU tracker keeps it inside its exchange record, whose rows are n_max apart)."""
+    assert t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[0] == 6, t.shape
+    assert t.stride(1) == 1 and t.stride(0) >= t.shape[1], t.stride()
+    return t
+
+
 # ---- particle filter ---------------------------------------------------------------------------
+@_on_device
 def init_particles(state, cx, cy, sigma_init, seed, stream_id=0, id_offset=0):
-    _dev(state, torch.float32)
+    _state(state)
     n = state.shape[1]
     _lib.check(_lib.load().vpf_init_particles(state.data_ptr(), n, state.stride(0), cx, cy,
                                               sigma_init, seed, stream_id, id_offset, _stream()),
                "vpf_init_particles")
 
 
+@_on_device
 def propagate(state, sigma_pos, sigma_vel, sigma_scale, seed, frame_idx, stream_id=0, id_offset=0):
-    _dev(state, torch.float32)
+    _state(state)
     n = state.shape[1]
     _lib.check(_lib.load().vpf_propagate(state.data_ptr(), n, state.stride(0), sigma_pos, sigma_vel,
                                          sigma_scale, seed, frame_idx, stream_id, id_offset,
                                          _stream()), "vpf_propagate")
 
 
+@_on_device
 def frame_advance(frame_idx_dev):
     _lib.check(_lib.load().vpf_frame_advance(frame_idx_dev.data_ptr(), _stream()), "vpf_frame_advance")
 
 
+@_on_device
 def propagate_dev(state, sigma_pos, sigma_vel, sigma_scale, seed, frame_idx_dev, stream_id=0,
                   id_offset=0):
-    _dev(state, torch.float32)
+    _state(state)
     _lib.check(_lib.load().vpf_propagate_dev(state.data_ptr(), state.shape[1], state.stride(0),
                                              sigma_pos, sigma_vel, sigma_scale, seed,
                                              frame_idx_dev.data_ptr(), stream_id, id_offset,
                                              _stream()), "vpf_propagate_dev")
 
 
+@_on_device
 def resample_dev(cdf_all, totals, n_local, id_offset, seed, stream_id, frame_idx_dev, state_all,
                  state_out, idx):
     _lib.check(_lib.load().vpf_resample_dev(cdf_all.data_ptr(), totals.data_ptr(), totals.numel(),
@@ -87,15 +118,17 @@ def resample_dev(cdf_all, totals, n_local, id_offset, seed, stream_id, frame_idx
 
 def philox_fill(n, id_offset, c1, c2, c3, seed, device="cuda"):
     out = torch.empty((4, n), dtype=torch.int32, device=device)
-    _lib.check(_lib.load().vpf_philox_fill(out.data_ptr(), n, id_offset, c1, c2, c3, seed,
-                                           _stream()), "vpf_philox_fill")
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.load().vpf_philox_fill(out.data_ptr(), n, id_offset, c1, c2, c3, seed,
+                                               _stream()), "vpf_philox_fill")
     return out
 
 
 def normals_fill(n, id_offset, frame_idx, stream_id, seed, device="cuda"):
     out = torch.empty((6, n), dtype=torch.float32, device=device)
-    _lib.check(_lib.load().vpf_normals_fill(out.data_ptr(), n, id_offset, frame_idx, stream_id,
-                                            seed, _stream()), "vpf_normals_fill")
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.load().vpf_normals_fill(out.data_ptr(), n, id_offset, frame_idx, stream_id,
+                                                seed, _stream()), "vpf_normals_fill")
     return out
 
 
@@ -104,9 +137,10 @@ def resample_uniform(seed, frame_idx, stream_id=0) -> float:
 
 
 # ---- crop --------------------------------------------------------------------------------------
+@_on_device
 def crop_state(frame, state, w0, h0, out=None, dtype=torch.bfloat16, crop_size=CROP):
     _dev(frame, torch.uint8)
-    _dev(state, torch.float32)
+    _state(state)
     H, W, _ = frame.shape
     n = state.shape[1]
     rows = n * n_patch(crop_size)
@@ -120,6 +154,7 @@ def crop_state(frame, state, w0, h0, out=None, dtype=torch.bfloat16, crop_size=C
     return out
 
 
+@_on_device
 def crop_boxes(frame, boxes, out=None, dtype=torch.bfloat16, crop_size=CROP):
     _dev(frame, torch.uint8)
     _dev(boxes, torch.float32)
@@ -136,6 +171,7 @@ def crop_boxes(frame, boxes, out=None, dtype=torch.bfloat16, crop_size=CROP):
 
 
 # ---- ViT stages (test hooks) ---------------------------------------------------------------------
+@_on_device
 def gemm_bf16(a, w, bias, mode, out=None, pos=None, patches_per_crop=N_PATCH):
     """C = A[M,K] @ W[N,K]^T with epilogue `mode` (see include/vpf.h)."""
     _dev(a, torch.bfloat16); _dev(w, torch.bfloat16); _dev(bias, torch.float32)
@@ -154,6 +190,7 @@ def gemm_bf16(a, w, bias, mode, out=None, pos=None, patches_per_crop=N_PATCH):
     return out
 
 
+@_on_device
 def layernorm(x, gamma, beta):
     _dev(x, torch.float32)
     rows, D = x.shape
@@ -163,6 +200,7 @@ def layernorm(x, gamma, beta):
     return out
 
 
+@_on_device
 def attention(qkv, n_crops, heads, tokens=TOKENS):
     _dev(qkv, torch.bfloat16)
     D = heads * 64
@@ -174,32 +212,57 @@ def attention(qkv, n_crops, heads, tokens=TOKENS):
 
 
 # ---- likelihood / normalisation / resampling ---------------------------------------------------
+@_on_device
 def loglik(emb, tmpl, tau, logw, local_max):
     n, D = emb.shape
     _lib.check(_lib.load().vpf_loglik(emb.data_ptr(), D, tmpl.data_ptr(), n, tau, logw.data_ptr(),
                                       local_max.data_ptr(), _stream()), "vpf_loglik")
 
 
+@_on_device
 def sumexp(logw, rank_max, local_sum):
     _lib.check(_lib.load().vpf_sumexp(logw.data_ptr(), logw.numel(), rank_max.data_ptr(),
                                       rank_max.numel(), local_sum.data_ptr(), _stream()),
                "vpf_sumexp")
 
 
-def weights(logw, rank_max, rank_sum, state, w, cdf_local, total_local, stats):
+@_on_device
+def weights(logw, rank_max, rank_sum, state, w, cdf_local, total_local, stats, accumulate=True):
+    """`accumulate=True`: stats += this shard's five sums (caller zeroes `stats` first);
+    False: stats is overwritten (one shard per vector: no zeroing kernel needed)."""
     _lib.check(_lib.load().vpf_weights(logw.data_ptr(), logw.numel(), rank_max.data_ptr(),
                                        rank_sum.data_ptr(), rank_max.numel(), state.data_ptr(),
                                        state.stride(0), w.data_ptr(), cdf_local.data_ptr(),
-                                       total_local.data_ptr(), stats.data_ptr(), _stream()),
+                                       total_local.data_ptr(), stats.data_ptr(),
+                                       1 if accumulate else 0, _stream()),
                "vpf_weights")
 
 
+@_on_device
 def resample(cdf_all, totals, n_local, id_offset, u, state_all, state_out, idx):
     R = totals.numel()
     _lib.check(_lib.load().vpf_resample(cdf_all.data_ptr(), totals.data_ptr(), R, n_local,
                                         id_offset, u, state_all.data_ptr(), state_out.data_ptr(),
                                         state_out.stride(0), idx.data_ptr(), _stream()),
                "vpf_resample")
+
+
+RECORD_HEADER = 8        # VPF_RECORD_HEADER in include/vpf.h
+
+
+@_on_device
+def resample_records(records, n_max, shard_off, n_local, id_offset, u, state_out, idx,
+                     stats_out=None, frame_idx_dev=None, seed=0, stream_id=0):
+    """Multi-GPU form: `records` f64 [R][rec_len] is the all-gather's receive buffer, read in
+    place (layout in include/vpf.h); `shard_off` int32 [R+1] on the device."""
+    R, rec_len = records.shape
+    assert records.dtype == torch.float64 and records.is_contiguous()
+    assert shard_off.dtype == torch.int32 and shard_off.numel() == R + 1
+    _lib.check(_lib.load().vpf_resample_records(
+        records.data_ptr(), rec_len, n_max, shard_off.data_ptr(), R, n_local, id_offset,
+        0.0 if u is None else float(u), _lib.ptr(frame_idx_dev), seed, stream_id,
+        state_out.data_ptr(), state_out.stride(0), idx.data_ptr(), _lib.ptr(stats_out), _stream()),
+        "vpf_resample_records")
 
 
 # ---- ViT encoder handle --------------------------------------------------------------------------
@@ -228,12 +291,15 @@ class VitEncoder:
                                   _lib.RESIDUAL_F16 if residual_dtype == torch.float16
                                   else _lib.RESIDUAL_F32)
         self._h = C.c_void_p()
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         _lib.check(lib.vpf_vit_create(C.byref(self._h), C.byref(self.cfg)), "vpf_vit_create")
-        self.weights = [t.to(device).contiguous() for t in packed_weights]   # keep alive
+        self.weights = [t.to(self.device).contiguous() for t in packed_weights]   # keep alive
         arr = (C.c_void_p * len(self.weights))(*[t.data_ptr() for t in self.weights])
         _lib.check(lib.vpf_vit_set_weights(self._h, arr, len(self.weights)), "vpf_vit_set_weights")
         nbytes = lib.vpf_vit_workspace_bytes(C.byref(self.cfg))
-        self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
         base = self.workspace.data_ptr()
         aligned = (base + 1023) // 1024 * 1024
         _lib.check(lib.vpf_vit_set_workspace(self._h, aligned, nbytes), "vpf_vit_set_workspace")
@@ -241,8 +307,16 @@ class VitEncoder:
 
     def forward(self, patches, n_crops, emb=None):
         assert patches.is_cuda and patches.dtype == self.dtype and patches.is_contiguous()
+        if patches.device != self.device:
+            raise ValueError(f"patches live on {patches.device}, the encoder on {self.device}")
         if emb is None:
             emb = torch.empty((n_crops, self.dim), dtype=torch.float32, device=patches.device)
+        if self.device.index != torch.cuda.current_device():
+            with torch.cuda.device(self.device):
+                return self._forward(patches, n_crops, emb)
+        return self._forward(patches, n_crops, emb)
+
+    def _forward(self, patches, n_crops, emb):
         _lib.check(self._lib.vpf_vit_forward(self._h, patches.data_ptr(), n_crops, emb.data_ptr(),
                                              _stream()), "vpf_vit_forward")
         return emb

@@ -9,14 +9,17 @@ runs in libvpf.so's sm_100a kernels on the current CUDA stream -- there is no CP
 Step order (oracle/tracker.py, D11): propagate -> crop -> ViT -> weigh -> estimate ->
 resample -> gather.  ``init`` is frame 0, the first ``step`` is frame 1.
 
-Multi-GPU (``process_group``): particles are sharded by global id, rank r owns
-[r*n_local, (r+1)*n_local).  Per frame: all-gather of the local log-weight maxima, all-gather
-of the exact local exp-sums, and one all-gather of (weight total | local CDF | state) that
-feeds the global resampling CDF.  Every quantity exchanged is exact (max, grid-snapped fp64
-sums), so the particle trajectory is bit-identical for any number of ranks.
+Multi-GPU (``process_group``): particles are sharded by global id (equal shards, or explicit
+``shards`` so a slower GPU carries fewer).  Per frame three collectives: all-gather of the local
+log-weight maxima, all-gather of the exact local exp-sums, and one all-gather of the packed
+record (weight total | estimate sums | local CDF | state) that the resampling kernel reads in
+place.  Every quantity exchanged is exact (max, grid-snapped fp64 sums), so the particle
+trajectory is bit-identical for any number of ranks and any split.  ``cuda_graph=True`` captures
+the whole device side of a frame -- the NCCL collectives included -- into one graph.
 """
 from __future__ import annotations
 
+import functools
 import math
 import os
 from typing import NamedTuple
@@ -25,7 +28,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .exchange import Exchange, shard_range
+from .exchange import Exchange, shard_range, shard_sizes
 from .vit_weights import VIT_CONFIGS, init_state_dict, pack_for_device
 
 
@@ -47,6 +50,22 @@ class _Stage:
         return False
 
 
+def _on_own_device(method):
+    """Runs a Tracker method with the tracker's device current (a process may drive several
+    GPUs; libvpf launches on the current device's stream)."""
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        if self.device.index != torch.cuda.current_device():
+            with torch.cuda.device(self.device):
+                return method(self, *args, **kwargs)
+        return method(self, *args, **kwargs)
+    return wrapper
+
+
+#: the exact fp64 exp-sum of the normalisation (2^-36 grid) needs log2(N) + 36 <= 53
+MAX_PARTICLES = 1 << 17
+
+
 class State(NamedTuple):
     bbox: tuple      # (x, y, w, h) top-left, pixels
     ess: float
@@ -57,7 +76,8 @@ class Tracker:
     def __init__(self, model="vit_base_patch16_224", n_particles=4096, seed=0, device="cuda",
                  dtype=torch.bfloat16, tau=0.1, sigma_pos=None, sigma_vel=None, sigma_scale=0.01,
                  sigma_init=None, state_dict=None, process_group=None, stream_id=0,
-                 encoder=None, cuda_graph=False, crop_size=224, residual_dtype=torch.float32):
+                 encoder=None, cuda_graph=False, crop_size=224, residual_dtype=torch.float32,
+                 shards=None):
         if not torch.cuda.is_available():
             raise RuntimeError("Tracker needs a CUDA device: the hot path has no CPU fallback")
         if dtype not in (torch.bfloat16, torch.float16):
@@ -72,6 +92,14 @@ class Tracker:
             raise ValueError(f"unknown model {model!r}; choose from {sorted(VIT_CONFIGS)}")
         self.model = model
         self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if not 0 < int(n_particles) <= MAX_PARTICLES:
+            raise ValueError(f"n_particles must be in [1, {MAX_PARTICLES}]: the order-independent "
+                             "fp64 exp-sum that makes sharded and single-GPU runs bit-identical "
+                             "is exact only while log2(N) + 36 <= 53")
         self.seed = int(seed)
         self.tau = float(tau)
         self.stream_id = int(stream_id)
@@ -83,7 +111,8 @@ class Tracker:
         else:
             self.rank, self.world = 0, 1
         self.n_global = int(n_particles)
-        self.id_offset, self.n = shard_range(self.n_global, self.rank, self.world)
+        self.shards = shard_sizes(self.n_global, self.world, shards)
+        self.id_offset, self.n = shard_range(self.n_global, self.rank, self.world, self.shards)
         cfg = VIT_CONFIGS[model]
         self.dim = cfg["dim"]
         if encoder is None:
@@ -95,28 +124,38 @@ class Tracker:
         assert encoder.max_crops >= self.n and encoder.dtype == dtype
         assert encoder.crop_size == self.crop_size
         self.encoder = encoder
-        dev, n, R = self.device, self.n, self.world
+        dev, n = self.device, self.n
         f32, f64 = torch.float32, torch.float64
-        self.particles = torch.zeros((6, n), dtype=f32, device=dev)
-        self._next = torch.zeros((6, n), dtype=f32, device=dev)
+        self.xch = Exchange(self.pg, n, dev, self.shards)
+        if self.world > 1:
+            # the rank's particle state lives inside its exchange record (nothing is copied before
+            # the all-gather) and resampling writes the children straight back into it
+            self.particles = self.xch.state_view()
+            self._next = None
+        else:
+            self.particles = torch.zeros((6, n), dtype=f32, device=dev)
+            self._next = torch.zeros((6, n), dtype=f32, device=dev)
         self.weights = torch.full((n,), 1.0 / self.n_global, dtype=f32, device=dev)
         self.patches = torch.empty((n * self.n_patch, ops.PATCH_K), dtype=dtype, device=dev)
         self.emb = torch.empty((n, self.dim), dtype=f32, device=dev)
         self.logw = torch.empty((n,), dtype=f32, device=dev)
         self.idx = torch.empty((n,), dtype=torch.int32, device=dev)
         self.template = torch.zeros((self.dim,), dtype=f32, device=dev)
-        self.xch = Exchange(self.pg, n, dev)
         self._stats = torch.zeros((5,), dtype=f64, device=dev)
         self._tbox = torch.empty((1, 4), dtype=f32, device=dev)
         self.frame_idx = -1
         self._pending = False
-        # CUDA-graph mode (single GPU): the whole device side of a step is captured once and
-        # replayed per frame; the frame counter and the resampling uniform then live on the device
-        self.use_graph = bool(cuda_graph) and self.world == 1
+        # CUDA-graph mode: the whole device side of a step (collectives included) is captured once
+        # and replayed per frame; the frame counter and the resampling uniform live on the device
+        self.use_graph = bool(cuda_graph)
         self._graph = None
         self._frame_buf = None
         self._fidx = torch.zeros((1,), dtype=torch.int32, device=dev)
         self.propagated = None
+        # per-frame device timing (bench.py, multi-GPU limiter analysis): events after the encoder
+        # and after resampling; off by default
+        self.timing = False
+        self._ev = None
 
     # -- helpers -----------------------------------------------------------------------------
     def _to_device_frame(self, frame):
@@ -130,6 +169,7 @@ class Tracker:
         return frame.contiguous()
 
     # -- API ---------------------------------------------------------------------------------
+    @_on_own_device
     def init(self, frame, bbox) -> None:
         frame = self._to_device_frame(frame)
         x, y, w, h = [float(v) for v in bbox]
@@ -161,6 +201,7 @@ class Tracker:
         self.step_begin(frame, _u, _emb)
         return self.step_end()
 
+    @_on_own_device
     def step_begin(self, frame, _u=None, _emb=None) -> None:
         """Enqueues the whole device side of one frame on the current stream and returns without
         waiting; `step_end()` reads the estimate back.  Lets a caller do host work (decode, stage the
@@ -177,46 +218,85 @@ class Tracker:
         self.frame_idx += 1
         if self.use_graph:
             self._fidx.fill_(self.frame_idx)      # keep the device counter in step (hook calls)
-        t = self.frame_idx
-        st = self.particles
+        u = ops.resample_uniform(self.seed, self.frame_idx, self.stream_id) if _u is None \
+            else float(_u)
+        self._device_step(frame, self.frame_idx, u, _emb)
+        self.last_u = u
+        self._pending = True
+
+    def _device_step(self, frame, t, u, emb_in=None):
+        """Device side of one frame.  `t` / `u` are host scalars on the eager path; both None means
+        the captured-graph form: static pointers, frame counter and resampling uniform taken from
+        the device counter `_fidx`, no host-supplied per-frame values."""
+        xch, st, on_dev = self.xch, self.particles, t is None
+        if self.timing:
+            self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            self._ev[0].record()
         # a3 motion
         with _Stage("K3a propagate"):
-            ops.propagate(st, self.sigma_pos, self.sigma_vel, self.sigma_scale, self.seed, t,
-                          self.stream_id, self.id_offset)
+            if on_dev:
+                ops.frame_advance(self._fidx)
+                ops.propagate_dev(st, self.sigma_pos, self.sigma_vel, self.sigma_scale, self.seed,
+                                  self._fidx, self.stream_id, self.id_offset)
+            else:
+                ops.propagate(st, self.sigma_pos, self.sigma_vel, self.sigma_scale, self.seed, t,
+                              self.stream_id, self.id_offset)
         # a4 crop, a5 ViT
-        if _emb is None:
+        if emb_in is None:
             with _Stage("K1 crop"):
                 ops.crop_state(frame, st, self.w0, self.h0, self.patches, crop_size=self.crop_size)
             with _Stage("K2 ViT encoder"):
                 self.encoder.forward(self.patches, self.n, self.emb)
             emb = self.emb
         else:
-            emb = _emb
+            emb = emb_in
+        if self.timing:
+            self._ev[1].record()
         # a6 likelihood + exact normalisation (collectives are no-ops on a single GPU)
-        xch = self.xch
+        fdev = self._fidx if on_dev else None
         with _Stage("K3b weigh + normalise"):
             ops.loglik(emb, self.template, self.tau, self.logw, xch.max_local)
             max_all = xch.gather_max()
             ops.sumexp(self.logw, max_all, xch.sum_local)
             sum_all = xch.gather_sum()
-            total, cdf, st_slot = xch.local_views()
-            self._stats.zero_()
-            ops.weights(self.logw, max_all, sum_all, st, self.weights, cdf, total, self._stats)
+            total, cdf, _ = xch.local_views()
+            stats = xch.stats_view() if self.world > 1 else self._stats
+            ops.weights(self.logw, max_all, sum_all, st, self.weights, cdf, total, stats,
+                        accumulate=False)
         # a7 + a8 resample + gather
-        u = ops.resample_uniform(self.seed, t, self.stream_id) if _u is None else float(_u)
         with _Stage("K4 resample + gather"):
             if self.world > 1:
-                st_slot.copy_(st)
-                totals, cdf_all, state_all = xch.gather_records()
-                xch.reduce_stats(self._stats)
+                # one all-gather of the packed records; the kernel reads the receive buffer in
+                # place, sums the ranks' estimate terms and writes this rank's children back into
+                # its own record (the gather has already consumed it)
+                rec_all = xch.gather_records()
+                ops.resample_records(rec_all, xch.n_max, xch.shard_off, self.n, self.id_offset, u,
+                                     st, self.idx, stats_out=self._stats, frame_idx_dev=fdev,
+                                     seed=self.seed, stream_id=self.stream_id)
+                self.propagated = None
+            elif on_dev:
+                ops.resample_dev(cdf, total, self.n, self.id_offset, self.seed, self.stream_id,
+                                 self._fidx, st, self._next, self.idx)
+                st.copy_(self._next)               # keeps every pointer of the graph static
             else:
-                totals, cdf_all, state_all = total, cdf, st
-            ops.resample(cdf_all, totals, self.n, self.id_offset, u, state_all, self._next, self.idx)
-        self.particles, self._next = self._next, self.particles
-        self.propagated = self._next            # pre-resampling state of this frame (tests)
-        self.last_u = u
-        self._pending = True
+                ops.resample(cdf, total, self.n, self.id_offset, u, st, self._next, self.idx)
+                if self.use_graph:
+                    # a captured graph holds these pointers: keep them static
+                    st.copy_(self._next)
+                    self.propagated = None
+                else:
+                    self.particles, self._next = self._next, st
+                    self.propagated = st           # pre-resampling state of this frame (tests)
+        if self.timing:
+            self._ev[2].record()
 
+    def last_timing(self):
+        """(encoder side ms, exchange + resampling ms) of the last eager frame; needs
+        `timing = True` and a synchronised device."""
+        e = self._ev
+        return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+
+    @_on_own_device
     def step_end(self) -> State:
         """Estimate of the frame enqueued by `step_begin`: the only device->host read of a step."""
         if not self._pending:
@@ -258,27 +338,9 @@ class Tracker:
         self._graph = None
 
     # -- CUDA-graph path ----------------------------------------------------------------------
-    def _device_step(self):
-        """Device side of one frame with static pointers and no host-supplied scalars."""
-        xch, st = self.xch, self.particles
-        ops.frame_advance(self._fidx)
-        ops.propagate_dev(st, self.sigma_pos, self.sigma_vel, self.sigma_scale, self.seed,
-                          self._fidx, self.stream_id, self.id_offset)
-        ops.crop_state(self._frame_buf, st, self.w0, self.h0, self.patches,
-                       crop_size=self.crop_size)
-        self.encoder.forward(self.patches, self.n, self.emb)
-        ops.loglik(self.emb, self.template, self.tau, self.logw, xch.max_local)
-        ops.sumexp(self.logw, xch.max_all, xch.sum_local)
-        total, cdf, _ = xch.local_views()
-        self._stats.zero_()
-        ops.weights(self.logw, xch.max_all, xch.sum_all, st, self.weights, cdf, total, self._stats)
-        ops.resample_dev(cdf, total, self.n, self.id_offset, self.seed, self.stream_id, self._fidx,
-                         st, self._next, self.idx)
-        st.copy_(self._next)                       # keeps every pointer of the graph static
-
     def _enqueue_graph(self, frame) -> None:
         if isinstance(frame, np.ndarray):
-            frame = torch.from_numpy(frame)
+            frame = torch.from_numpy(np.ascontiguousarray(frame))   # e.g. a BGR->RGB flipped view
         if frame.dtype != torch.uint8 or frame.dim() != 3 or frame.shape[2] != 3:
             raise ValueError("frame must be uint8 [H, W, 3] RGB")
         if self._frame_buf is None or self._frame_buf.shape != frame.shape:
@@ -287,12 +349,17 @@ class Tracker:
         self._frame_buf.copy_(frame, non_blocking=True)
         self.frame_idx += 1
         if self._graph is None:
-            self._device_step()                    # first frame eagerly: sets kernel attributes,
-            torch.cuda.synchronize()               # builds tensor maps; then capture for replay
+            # first frame eagerly (sets kernel attributes, builds tensor maps, brings the NCCL
+            # communicator up); then capture for replay
+            timing, self.timing = self.timing, False
+            self._device_step(self._frame_buf, None, None)
+            torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._device_step()
+                self._device_step(self._frame_buf, None, None)
+            # capturing does not execute: the device counter has advanced once (the eager frame)
             self._graph = g
+            self.timing = timing
         else:
             self._graph.replay()
         self.last_u = ops.resample_uniform(self.seed, self.frame_idx, self.stream_id)
