@@ -47,6 +47,8 @@ PARTICLES_PER_GPU = 4096
 FRAME_HW = (1080, 1920)
 TARGET = (96, 96)
 CLIP_FRAMES = 16
+DEFAULT_RESIDUAL = "fp32"      # storage type of the residual stream in the headline run
+DEFAULT_SHARDS = "equal"       # particle split across GPUs in the headline run (N > 1)
 
 
 def load_peaks():
@@ -135,26 +137,35 @@ def cpu_oracle_run(steps, warmup, n_sample, frames, gt):
     return n_sample * steps / dt, dt / steps, threads
 
 
+REF_SAMPLE = 32          # particles the CPU arm tracks per step (of PARTICLES_PER_GPU)
+
+
 def run_reference(args, emit):
     """--impl reference: the reference's CPU implementation of the path.  The upstream repo is a
-    README only, so this is the oracle port (oracle/), with every host thread torch can use."""
+    README only, so this is the oracle port (oracle/), with every host thread torch can use.
+    Each step is a bounded SAMPLE of the workload: REF_SAMPLE of the 4096 particles through the
+    same clip (~0.8 s per step on 16 threads), so --steps / --warmup are honoured as given."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from vitparticlefiltertracker_b200.synthetic import make_clip
-    frames, gt = make_clip("box", FRAME_HW[0], FRAME_HW[1], 6, seed=0, target=TARGET,
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    frames, gt = make_clip("box", FRAME_HW[0], FRAME_HW[1], CLIP_FRAMES, seed=0, target=TARGET,
                            velocity=(3.0, 1.0))
-    n_sample = 32
-    steps = max(1, min(args.steps, 4))
-    warmup = max(0, min(args.warmup, 1))
-    v, sec, threads = cpu_oracle_run(steps, warmup, n_sample, frames, gt)
-    sample = (f"OracleTracker (CPU PyTorch fp32), {n_sample} of {PARTICLES_PER_GPU} particles, "
-              f"{steps} frames of the same 1080p clip")
+    v, sec, threads = cpu_oracle_run(steps, warmup, REF_SAMPLE, frames, gt)
+    sample = (f"OracleTracker (CPU PyTorch fp32, {threads} threads): {REF_SAMPLE} of "
+              f"{PARTICLES_PER_GPU} particles per step, {steps} timed + {warmup} warm-up frames of "
+              f"the same 1080p clip; value = particles tracked per second, i.e. the full "
+              f"4096-particle step would take {PARTICLES_PER_GPU / v:.0f} s")
+    cfg = workload_config(args.gpus)
+    cfg["workload"] += (f" -- CPU arm: a {REF_SAMPLE}-particle sample of it per step "
+                        "(per-particle cost is constant, the rate extrapolates linearly)")
+    cfg["particles_timed_per_step"] = REF_SAMPLE
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": cfg,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -163,24 +174,52 @@ def run_reference(args, emit):
     emit(line)
 
 
-def workload_config(n_gpus, model=MODEL):
+def workload_config(n_gpus, model=MODEL, ppg=PARTICLES_PER_GPU):
     name = ("BASELINE configs[2]: ViT-B/16 @224" if model == MODEL else
             f"BASELINE configs[3] shape ({model}; --model overrides the headline ViT-B/16)")
-    return {"workload": name + ", 4096 particles per GPU, systematic "
+    return {"workload": name + f", {ppg} particles per GPU, systematic "
                         "resampling every frame, synthetic 1080p moving-target clip",
-            "model": model, "particles_per_gpu": PARTICLES_PER_GPU,
-            "particles_total": PARTICLES_PER_GPU * n_gpus, "frame": "1080x1920x3 uint8",
+            "model": model, "particles_per_gpu": ppg,
+            "particles_total": ppg * n_gpus, "frame": "1080x1920x3 uint8",
             "parallelism": f"particle-sharded x{n_gpus}",
             "l2": "per-step working set ~10 GB per GPU >> 126 MB L2 (inputs larger than L2)"}
 
 
-def gemm_roofline(dev, M, D, peaks, reps=2):
+def source_hash(*names):
+    """sha256 over the kernel sources a capture depends on (stamped into profiles/ncu_gemm_*.json
+    by tools/summarize_ncu.py; a capture of another build is not reported as this build's)."""
+    import hashlib
+    h = hashlib.sha256()
+    for n in names:
+        h.update(open(os.path.join(ROOT, "vitparticlefiltertracker_b200", "csrc", n), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic():
+    """DRAM bytes of the GEMM family from the newest committed `ncu --set full` capture whose
+    source stamp matches the GEMM sources of this build; (None, why) otherwise."""
+    cur = source_hash("gemm.cuh", "sm100.cuh")
+    for name in ("ncu_gemm_r02.json", "ncu_gemm_r01.json"):
+        prof = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(prof):
+            continue
+        pj = json.load(open(prof))
+        if pj.get("source_sha16") != cur:
+            continue
+        return (pj["gemm_family_traffic_bytes_per_block"],
+                f"profiles/{name} (capture of git {pj.get('git_sha', '?')}, source stamp {cur}): "
+                "dram__bytes_read+write summed over the four launches of one block (ncu --set "
+                f"full); algorithmic bytes {pj['gemm_family_algorithmic_bytes_per_block']:.4g}")
+    return None, f"no committed ncu capture matches this build's GEMM sources (stamp {cur})"
+
+
+def gemm_roofline(dev, M, D, peaks, reps=2, x16=False):
     """Times every GEMM launch of a 12-block encoder pass (qkv, proj, fc1, fc2 at the real M)
     with CUDA events on the launching stream, inside a sustained loop."""
     from vitparticlefiltertracker_b200 import ops
     xn = (torch.randn(M, D, device=dev) * 0.5).to(torch.bfloat16)
     big = torch.empty(M, 4 * D, dtype=torch.bfloat16, device=dev)
-    X = torch.zeros(M, D, device=dev)
+    X = torch.zeros(M, D, device=dev, dtype=torch.float16 if x16 else torch.float32)
     shapes = [("qkv", 3 * D, D, 0), ("proj", D, D, 2), ("fc1", 4 * D, D, 1), ("fc2", D, 4 * D, 2)]
     ws = {n: ((torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16),
               torch.zeros(N, device=dev)) for n, N, K, _ in shapes}
@@ -216,13 +255,8 @@ def gemm_roofline(dev, M, D, peaks, reps=2):
     achieved = tot_fl / tot_ms / 1e9
     peak = peaks["tflops_sustained"]
     traffic, traffic_src = None, None
-    prof = os.path.join(ROOT, "profiles", "ncu_gemm_r01.json")
-    if os.path.exists(prof) and M == 4096 * 197 and D == 768:     # captured on this exact shape
-        pj = json.load(open(prof))
-        traffic = pj["gemm_family_traffic_bytes_per_block"]
-        traffic_src = ("profiles/ncu_gemm_r01.json: dram__bytes_read+write summed over the four "
-                       "launches of one block (ncu --set full); algorithmic bytes "
-                       f"{pj['gemm_family_algorithmic_bytes_per_block']:.4g}")
+    if M == 4096 * 197 and D == 768:                       # captures are of this exact shape
+        traffic, traffic_src = ncu_traffic()
     return {"bound": "tensor", "kernel": "gemm_bf16_kernel<tcgen05, cta_group::2> (qkv+proj+fc1+fc2 of one block)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_burst": peaks["tflops_burst"], "frac_of_burst_peak": achieved / peaks["tflops_burst"],
@@ -340,12 +374,12 @@ def native_resolution_point(dev, frames_dev, frames_host, gt, op_dtype, crop_siz
     return res
 
 
-def residual16_point(dev, frames_dev, gt, op_dtype, steps=8, warmup=3):
-    """The headline workload with the encoder's residual stream stored in fp16 (VPF_RESIDUAL_F16,
-    DESIGN.md section 6-0) instead of fp32: informative, not the headline."""
+def alt_point(dev, frames_dev, gt, op_dtype, res_dtype, note, steps=8, warmup=3):
+    """The headline workload at another operating point (operand type / residual-stream type):
+    informative, measured in the same run, not the headline."""
     from vitparticlefiltertracker_b200 import Tracker
     n = PARTICLES_PER_GPU
-    trk = Tracker(MODEL, n, seed=0, device=dev, dtype=op_dtype, residual_dtype=torch.float16)
+    trk = Tracker(MODEL, n, seed=0, device=dev, dtype=op_dtype, residual_dtype=res_dtype)
     trk.init(frames_dev[0], gt[0])
     for i in range(warmup):
         trk.step(frames_dev[1 + i % (CLIP_FRAMES - 1)])
@@ -357,10 +391,11 @@ def residual16_point(dev, frames_dev, gt, op_dtype, steps=8, warmup=3):
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / steps
+    del trk
+    torch.cuda.empty_cache()
     return {"ms_per_step": ms, "frames_per_s": 1e3 / ms, "particle_updates_per_s": n * 1e3 / ms,
-            "steps": steps,
-            "note": "informative operating point, not the headline: fp16 residual stream (half the "
-                    "residual bytes, +2 % distance to the fp32 oracle; tests/test_gpu_residual16.py)"}
+            "steps": steps, "operands": str(op_dtype).replace("torch.", ""),
+            "residual": str(res_dtype).replace("torch.", ""), "note": note}
 
 
 def main():
@@ -377,6 +412,17 @@ def main():
                     help="skip the informative crop-size-64 operating point")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
                     help="16-bit operand type of the encoder (fp32 accumulation either way)")
+    ap.add_argument("--residual", default=DEFAULT_RESIDUAL, choices=["fp32", "fp16"],
+                    help="storage type of the encoder's residual stream")
+    ap.add_argument("--shards", default=DEFAULT_SHARDS, choices=["equal", "balanced"],
+                    help="N > 1: equal particle shards, or shards sized from a 3-step calibration "
+                         "so that a slower (power-capped) GPU carries fewer particles")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay each step as one captured CUDA graph (NCCL collectives included)")
+    ap.add_argument("--particles-per-gpu", type=int, default=PARTICLES_PER_GPU)
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the informative operating points (fp16 operands, other residual "
+                         "type, native resolution) and the CPU baseline")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything a library writes to fd 1 (the NCCL version
     # banner, for one) is sent to stderr, and the line itself goes out through a private copy
@@ -409,7 +455,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     n_gpus = world
-    n_total = PARTICLES_PER_GPU * n_gpus
+    n_total = args.particles_per_gpu * n_gpus
     peaks = load_peaks()
 
     frames, gt = make_clip("box", FRAME_HW[0], FRAME_HW[1], CLIP_FRAMES, seed=0, target=TARGET,
@@ -417,28 +463,71 @@ def main():
     frames_host = torch.from_numpy(frames).pin_memory()
     frames_dev = torch.from_numpy(frames).to(dev)
     op_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
-    trk = Tracker(args.model, n_total, seed=0, device=dev, process_group=pg, dtype=op_dtype)
-    trk.init(frames_dev[0], gt[0])
+    res_dtype = torch.float16 if args.residual == "fp16" else torch.float32
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    ious = []
+    def make_tracker(shards=None, graph=False):
+        t = Tracker(args.model, n_total, seed=0, device=dev, process_group=pg, dtype=op_dtype,
+                    residual_dtype=res_dtype, shards=shards, cuda_graph=graph)
+        t.init(frames_dev[0], gt[0])
+        return t
 
-    def timed(frames_src, steps, warmup):
+    def rank_stats(vals):
+        """min / median / max over ranks of a per-rank scalar (all ranks call this)."""
+        t = torch.tensor([float(vals)], device=dev, dtype=torch.float64)
+        if world > 1:
+            out = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(out, t)
+            v = [float(x.item()) for x in out]
+        else:
+            v = [float(t.item())]
+        return {"min": min(v), "median": float(np.median(v)), "max": max(v), "per_rank": v}
+
+    shards, calibration = None, None
+    if world > 1 and args.shards == "balanced":
+        # 3 timed steps with equal shards; each rank's encoder-side time (events around propagate,
+        # crop and the ViT: no collective inside) sizes its shard for the real run
+        cal = make_tracker()
+        cal.timing = True
+        comp = []
+        for i in range(5):
+            cal.step(frames_dev[1 + i])
+            torch.cuda.synchronize()
+            if i >= 2:
+                comp.append(cal.last_timing()[0])
+        st = rank_stats(float(np.mean(comp)))
+        from vitparticlefiltertracker_b200.exchange import balanced_shards
+        shards = balanced_shards(n_total, st["per_rank"], quantum=8)
+        calibration = {"compute_ms_equal_shards": st, "shards": shards}
+        del cal
+        torch.cuda.empty_cache()
+        barrier()
+    trk = make_tracker(shards, args.graph)
+
+    ious, t_comp, t_xch = [], [], []
+
+    def timed(frames_src, steps, warmup, record=False):
         for i in range(warmup):
             f = 1 + i % (CLIP_FRAMES - 1)
             ious.append(iou(trk.step(frames_src[f]).bbox, gt[f]))
         barrier()
+        trk.timing = record and not args.graph
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for i in range(steps):
             f = 1 + (warmup + i) % (CLIP_FRAMES - 1)
             ious.append(iou(trk.step(frames_src[f]).bbox, gt[f]))
+            if trk.timing:               # step() has just read the estimate back: events are done
+                c, x = trk.last_timing()
+                t_comp.append(c)
+                t_xch.append(x)
         e.record()
         barrier()
+        trk.timing = False
         ms = torch.tensor([s.elapsed_time(e)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -447,17 +536,42 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(frames_dev, args.steps, args.warmup)
+    ms_dev = timed(frames_dev, args.steps, args.warmup, record=True)
     ms_e2e = timed(frames_host, args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
+    per_rank = None
+    if t_comp:
+        # where a multi-GPU step's time goes, per rank: the encoder side (propagate + crop + ViT,
+        # no collective) and everything after it (likelihood, three collectives, resampling) --
+        # on a fast rank the latter is mostly WAITING for the slowest rank's first all-gather
+        per_rank = {"compute_ms": rank_stats(float(np.mean(t_comp))),
+                    "exchange_and_wait_ms": rank_stats(float(np.mean(t_xch)))}
+        c, x = per_rank["compute_ms"], per_rank["exchange_and_wait_ms"]
+        per_rank["collective_floor_ms"] = x["min"]
+        per_rank["straggler_spread_ms"] = c["max"] - c["min"]
+        per_rank["limiter"] = None if world == 1 else (
+            "straggler: the slowest rank's encoder time paces every rank (spread "
+            f"{c['max'] - c['min']:.2f} ms vs {x['min']:.2f} ms of collectives + PF kernels)"
+            if c["max"] - c["min"] > x["min"] else
+            f"exchange: collectives + PF kernels {x['min']:.2f} ms per step exceed the rank "
+            f"spread {c['max'] - c['min']:.2f} ms")
 
-    roof, gemm_ms = gemm_roofline(dev, trk.n * 197, trk.dim, peaks) if rank == 0 else (None, 0.0)
+    x16 = args.residual == "fp16"
+    roof, gemm_ms = gemm_roofline(dev, trk.n * 197, trk.dim, peaks, x16=x16) if rank == 0 else (None, 0.0)
     hbm = hbm_kernels(dev, trk, frames_dev[1], peaks) if rank == 0 else None
-    stages = stage_times(dev, trk, frames_dev[1]) if rank == 0 else None
-    native, res16 = None, None
-    if n_gpus == 1 and not args.no_native and args.model == MODEL:
-        native = native_resolution_point(dev, frames_dev, frames_host, gt, op_dtype)
-        res16 = residual16_point(dev, frames_dev, gt, op_dtype)
+    stages = stage_times(dev, trk, frames_dev[1]) if rank == 0 and not args.graph else None
+    extras = {}
+    if n_gpus == 1 and not args.no_extras and not args.no_native and args.model == MODEL \
+            and args.particles_per_gpu == PARTICLES_PER_GPU:
+        other_res = "fp32" if x16 else "fp16"
+        extras["fp16_operands" if args.dtype == "bf16" else "bf16_operands"] = alt_point(
+            dev, frames_dev, gt, torch.float16 if args.dtype == "bf16" else torch.bfloat16, res_dtype,
+            "same workload, the other 16-bit operand type (fp16: 8x closer to the fp32 oracle, "
+            "see BASELINE.md section 5; same tensor-core rate and bytes)")
+        extras["residual_" + other_res] = alt_point(
+            dev, frames_dev, gt, op_dtype, torch.float32 if x16 else torch.float16,
+            f"same workload with the residual stream stored in {other_res}")
+        extras["native_resolution"] = native_resolution_point(dev, frames_dev, frames_host, gt, op_dtype)
     barrier()
 
     tracking = {"mean_iou_vs_ground_truth": float(np.mean(ious[: args.warmup + args.steps])),
@@ -475,7 +589,10 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": workload_config(n_gpus, args.model),
+            "config": dict(workload_config(n_gpus, args.model, args.particles_per_gpu),
+                           operands=args.dtype, residual_stream=args.residual,
+                           shards=(trk.shards if n_gpus > 1 else None),
+                           cuda_graph=bool(args.graph)),
             "frames_per_s": args.steps / (ms_dev / 1e3),
             "step_tflops_per_gpu": trk.n * fl / (ms_step / 1e3) / 1e12,
             "step_frac_of_sustained_peak": trk.n * fl / (ms_step / 1e3) / 1e12 / peaks["tflops_sustained"],
@@ -486,15 +603,16 @@ def main():
             "roofline": roof, "hbm_kernels": hbm, "stages_ms": stages, "tracking": tracking,
             "clocks": clocks,
         }
-        if native is not None:
-            line["native_resolution"] = native
-            line["residual_fp16"] = res16
-        if n_gpus == 1 and not args.no_cpu_baseline and args.model == MODEL:
-            n_sample = 32
-            v, sec, threads = cpu_oracle_run(2, 1, n_sample, frames[:4], gt[:4])
+        line.update(extras)
+        if per_rank is not None:
+            line["per_rank"] = per_rank
+        if calibration is not None:
+            line["calibration"] = calibration
+        if n_gpus == 1 and not args.no_cpu_baseline and not args.no_extras and args.model == MODEL:
+            v, sec, threads = cpu_oracle_run(2, 1, REF_SAMPLE, frames[:4], gt[:4])
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": f"OracleTracker (CPU PyTorch fp32): {n_sample} of {PARTICLES_PER_GPU} "
+                "sample": f"OracleTracker (CPU PyTorch fp32): {REF_SAMPLE} of {PARTICLES_PER_GPU} "
                           f"particles, 2 timed frames of the same clip ({sec:.1f} s/frame)"}
         emit(line)
     if world > 1:

@@ -33,7 +33,7 @@ def main(path="config.yaml"):
         bbox = inp.get("bbox")
         if bbox is None:
             raise SystemExit(f"input.bbox (x, y, w, h of the target in the first frame) is required for {kind} input")
-    sd = torch.load(cfg["checkpoint"], map_location="cpu") if cfg.get("checkpoint") else None
+    sd = cfg.get("checkpoint") or None      # a path: Tracker -> vit_weights.load_checkpoint
     dtype = torch.float16 if cfg.get("dtype", "bf16") == "fp16" else torch.bfloat16
     trk = Tracker(cfg.get("model", "vit_base_patch16_224"), cfg.get("n_particles", 4096),
                   seed=cfg.get("seed", 0), tau=cfg.get("tau", 0.1), sigma_pos=cfg.get("sigma_pos"),

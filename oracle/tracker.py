@@ -16,7 +16,7 @@ import numpy as np
 from . import pf
 from .crop import boxes_from_state, crop_resize
 from .philox import philox_uniform53
-from .vit import init_vit_weights, vit_forward
+from .vit import init_vit_weights, normalise_state_dict, vit_forward
 
 
 class State(NamedTuple):
@@ -38,7 +38,8 @@ class OracleTracker:
         self.tau = float(tau)
         self.stream_id = int(stream_id)
         self._sig = (sigma_pos, sigma_vel, sigma_scale, sigma_init)
-        self.sd = state_dict if state_dict is not None else init_vit_weights(model)
+        self.sd = (normalise_state_dict(state_dict, model) if state_dict is not None
+                   else init_vit_weights(model))
         self.vit_chunk = vit_chunk
         self.crop_size = int(crop_size)     # 224, or a smaller multiple of 16
         self.frame_idx = -1

@@ -104,10 +104,60 @@ def init_vit_weights(model: str, seed: int = WEIGHT_SEED) -> dict:
     return sd
 
 
+def normalise_state_dict(sd: dict, model: str) -> dict:
+    """What a real timm checkpoint needs before the forward below can use it: unwrap a
+    ``{"state_dict": ...}`` / ``{"model": ...}`` container, strip a ``module.`` prefix, drop the
+    keys the tracker has no use for (``head.*``, ``fc_norm.*``, ...), check shapes, convert
+    fp16 / bf16 tensors to fp32."""
+    for k in ("state_dict", "model"):
+        if k in sd and isinstance(sd[k], dict):
+            sd = sd[k]
+    sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+    out = {}
+    for key, shape, _ in weight_keys(model):
+        if key not in sd:
+            raise KeyError(f"checkpoint has no {key!r} (expected timm {model} key names)")
+        t = torch.as_tensor(sd[key]).detach().to(torch.float32)
+        if key == "pos_embed":
+            if t.dim() != 3 or t.shape[0] != 1 or t.shape[2] != shape[2]:
+                raise ValueError(f"pos_embed has shape {tuple(t.shape)}")
+        elif tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{key} has shape {tuple(t.shape)}, {model} needs {tuple(shape)}")
+        out[key] = t.contiguous()
+    return out
+
+
+# ---- operand-precision emulation (study tool for SURVEY.md section 8f-2 "FP8 GEMMs") ----------
+E4M3_MAX = 448.0
+
+
+def quantise(t: torch.Tensor, fmt):
+    """Rounds a GEMM operand to `fmt` and back to fp32: None (fp32), "bf16", "fp16", or "e4m3"
+    (per-tensor scale amax -> 448, round-to-nearest-even to float8_e4m3fn, the recipe a
+    `tcgen05.mma.kind::f8f6f4` path with per-tensor scaling would use)."""
+    if fmt is None:
+        return t
+    if fmt == "bf16":
+        return t.to(torch.bfloat16).to(torch.float32)
+    if fmt == "fp16":
+        return t.to(torch.float16).to(torch.float32)
+    if fmt == "e4m3":
+        amax = t.abs().max().clamp_min(1e-12)
+        s = E4M3_MAX / amax
+        return (t * s).to(torch.float8_e4m3fn).to(torch.float32) / s
+    raise ValueError(f"unknown operand format {fmt!r}")
+
+
 @torch.no_grad()
-def vit_forward(crops, sd: dict, model: str, chunk: int = 32, return_tokens: bool = False):
+def vit_forward(crops, sd: dict, model: str, chunk: int = 32, return_tokens: bool = False,
+                linear_fmt=None, attn_fmt=None):
     """crops fp32 [N,3,S,S] (numpy or torch; S = 224, or a smaller multiple of 16 with the
-    position embedding resampled to the (S/16)^2 grid) -> CLS embedding fp32 [N,D] (numpy)."""
+    position embedding resampled to the (S/16)^2 grid) -> CLS embedding fp32 [N,D] (numpy).
+
+    `linear_fmt` / `attn_fmt` (default None = the fp32 oracle) emulate reduced-precision GEMM
+    operands with fp32 accumulation -- the patch-embed / qkv / proj / fc1 / fc2 contractions and
+    the two attention contractions respectively (see `quantise`); a CPU study tool
+    (tools/fp8_study.py), not a code path of the tracker."""
     c = VIT_CONFIGS[model]
     d, depth, heads = c["dim"], c["depth"], c["heads"]
     hd = d // heads
@@ -115,27 +165,42 @@ def vit_forward(crops, sd: dict, model: str, chunk: int = 32, return_tokens: boo
     grid = x_all.shape[-1] // 16
     TOKENS = grid * grid + 1                                   # noqa: N806 (197 at S = 224)
     pos_embed = resample_pos_embed(sd["pos_embed"], grid)
+    qw = {}
+
+    def lin(h, wkey, bkey):
+        if linear_fmt is None:
+            return F.linear(h, sd[wkey], sd[bkey])
+        if wkey not in qw:
+            qw[wkey] = quantise(sd[wkey], linear_fmt)
+        return F.linear(quantise(h, linear_fmt), qw[wkey], sd[bkey])
+
     outs = []
     for s in range(0, x_all.shape[0], chunk):
         x = x_all[s:s + chunk]
         n = x.shape[0]
-        x = F.conv2d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=16)
+        if linear_fmt is None:
+            x = F.conv2d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=16)
+        else:      # crops reach the GPU GEMM as 16-bit patches: keep them at least that coarse
+            x = F.conv2d(quantise(x, "bf16" if linear_fmt == "e4m3" else linear_fmt),
+                         quantise(sd["patch_embed.proj.weight"], "bf16" if linear_fmt == "e4m3"
+                                  else linear_fmt), sd["patch_embed.proj.bias"], stride=16)
         x = x.flatten(2).transpose(1, 2)                       # [n,P,D], patch index = py*grid+px
         x = torch.cat([sd["cls_token"].expand(n, -1, -1), x], dim=1) + pos_embed
         for i in range(depth):
             p = f"blocks.{i}."
             h = F.layer_norm(x, (d,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], LN_EPS)
-            qkv = F.linear(h, sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"])
+            qkv = lin(h, p + "attn.qkv.weight", p + "attn.qkv.bias")
+            qkv = quantise(qkv, attn_fmt)
             qkv = qkv.reshape(n, TOKENS, 3, heads, hd).permute(2, 0, 3, 1, 4)
             q, k, v = qkv[0], qkv[1], qkv[2]                   # [n,H,T,hd]
             att = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(hd))
             att = att.softmax(dim=-1)
-            o = (att @ v).transpose(1, 2).reshape(n, TOKENS, d)
-            x = x + F.linear(o, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"])
+            o = (quantise(att, attn_fmt) @ v).transpose(1, 2).reshape(n, TOKENS, d)
+            x = x + lin(o, p + "attn.proj.weight", p + "attn.proj.bias")
             h = F.layer_norm(x, (d,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], LN_EPS)
-            h = F.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])
+            h = lin(h, p + "mlp.fc1.weight", p + "mlp.fc1.bias")
             h = F.gelu(h)                                      # exact (erf) GELU
-            x = x + F.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+            x = x + lin(h, p + "mlp.fc2.weight", p + "mlp.fc2.bias")
         if return_tokens:
             outs.append(x)
         else:

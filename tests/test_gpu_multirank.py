@@ -53,3 +53,50 @@ def test_sharded_pf_step_is_rank_invariant(R):
     s1, w1, i1, o1 = run(1)
     sR, wR, iR, oR = run(R)
     assert torch.equal(s1, sR) and torch.equal(w1, wR) and torch.equal(i1, iR) and torch.equal(o1, oR)
+
+
+def test_tracker_on_a_non_current_device():
+    """a tracker built on cuda:1 while cuda:0 is current must launch on cuda:1 (libvpf
+    takes torch's current stream and keys its per-device state on cudaGetDevice)."""
+    from vitparticlefiltertracker_b200 import Tracker
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+    cuda()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    frames, gt = make_clip("box", 224, 224, 4, seed=0, target=(48, 48))
+    a = Tracker("vit_tiny_patch16_224", 64, seed=3, device="cuda:0")
+    b = Tracker("vit_tiny_patch16_224", 64, seed=3, device="cuda:1")     # cuda:0 stays current
+    a.init(frames[0], gt[0])
+    b.init(frames[0], gt[0])
+    assert b.particles.device.index == 1 and torch.cuda.current_device() == 0
+    for t in (1, 2, 3):
+        sa, sb = a.step(frames[t]), b.step(frames[t])
+        assert sa == sb and torch.equal(a.particles.cpu(), b.particles.cpu())
+    assert torch.cuda.current_device() == 0
+
+
+def test_graph_mode_survives_an_interleaved_hook_step():
+    """a hooked (eager) step between graph replays must not leave the captured graph
+    with stale pointers."""
+    from vitparticlefiltertracker_b200 import Tracker
+    from vitparticlefiltertracker_b200.synthetic import make_clip
+    cuda()
+    frames, gt = make_clip("box", 224, 224, 8, seed=1, target=(48, 48))
+    eager = Tracker("vit_tiny_patch16_224", 128, seed=5)
+    graph = Tracker("vit_tiny_patch16_224", 128, seed=5, cuda_graph=True)
+    eager.init(frames[0], gt[0])
+    graph.init(frames[0], gt[0])
+    for t in range(1, 8):
+        hook = {"_u": 0.25} if t in (3, 6) else {}
+        a, b = eager.step(frames[t], **hook), graph.step(frames[t], **hook)
+        assert torch.equal(eager.particles, graph.particles), t
+        assert torch.equal(eager.idx, graph.idx) and a == b
+    assert graph._graph is not None
+
+
+def test_particle_count_bound_is_enforced():
+    from vitparticlefiltertracker_b200 import Tracker
+    cuda()
+    with pytest.raises(ValueError, match="n_particles"):
+        Tracker("vit_tiny_patch16_224", (1 << 17) + 1)

@@ -4,7 +4,12 @@
 
 Every rank tracks its shard of N particles through the sharded Tracker; rank 0 additionally runs
 the same clip with ONE unsharded Tracker.  The gathered sharded particle set, the weights and the
-ancestor indices must equal the single-GPU run bit for bit."""
+ancestor indices must equal the single-GPU run bit for bit.
+
+    VPF_CHECK_SHARDS=uneven   unequal shard sizes (a slower GPU may carry fewer particles)
+    VPF_CHECK_GRAPH=1         the sharded tracker replays one captured CUDA graph per frame, NCCL
+                              collectives included
+    VPF_CHECK_CROP_SIZE=64    native-resolution crops"""
 import json
 import os
 import sys
@@ -27,7 +32,14 @@ def main():
     model, n, frames_n = "vit_tiny_patch16_224", 512, 5
     crop_size = int(os.environ.get("VPF_CHECK_CROP_SIZE", "224"))
     frames, gt = make_clip("box", 224, 224, frames_n, seed=0, target=(48, 48))
-    sharded = Tracker(model, n, seed=7, device=dev, process_group=dist.group.WORLD, crop_size=crop_size)
+    shards = None
+    if os.environ.get("VPF_CHECK_SHARDS", "equal") == "uneven":
+        w = np.array([3 + (r * 5) % 7 for r in range(world)], dtype=np.float64)
+        shards = [max(1, int(v)) for v in np.floor(n * w / w.sum())]
+        shards[-1] += n - sum(shards)
+    graph = os.environ.get("VPF_CHECK_GRAPH", "0") == "1"
+    sharded = Tracker(model, n, seed=7, device=dev, process_group=dist.group.WORLD, crop_size=crop_size,
+                      shards=shards, cuda_graph=graph)
     sharded.init(frames[0], gt[0])
     single = None
     if rank == 0:
@@ -36,12 +48,21 @@ def main():
     ok, report = True, []
     for f in range(1, frames_n):
         s = sharded.step(frames[f])
-        parts = [torch.empty_like(sharded.particles) for _ in range(world)]
-        ws = [torch.empty_like(sharded.weights) for _ in range(world)]
-        idxs = [torch.empty_like(sharded.idx) for _ in range(world)]
-        dist.all_gather(parts, sharded.particles.contiguous())
-        dist.all_gather(ws, sharded.weights)
-        dist.all_gather(idxs, sharded.idx)
+        sz = sharded.shards
+        parts = [torch.empty((6, k), device=dev) for k in sz]
+        ws = [torch.empty((k,), device=dev) for k in sz]
+        idxs = [torch.empty((k,), dtype=torch.int32, device=dev) for k in sz]
+        if len(set(sz)) == 1:
+            dist.all_gather(parts, sharded.particles.contiguous())
+            dist.all_gather(ws, sharded.weights)
+            dist.all_gather(idxs, sharded.idx)
+        else:                                   # uneven shards: one broadcast per rank
+            for r in range(world):
+                for buf, mine in ((parts, sharded.particles.contiguous()), (ws, sharded.weights),
+                                  (idxs, sharded.idx)):
+                    if r == rank:
+                        buf[r].copy_(mine)
+                    dist.broadcast(buf[r], src=r)
         if rank == 0:
             r = single.step(frames[f])
             same_p = torch.equal(torch.cat(parts, dim=1), single.particles)
@@ -53,6 +74,7 @@ def main():
             ok = ok and same_p and same_w and same_i and same_b
     if rank == 0:
         print(json.dumps({"world": world, "n_particles": n, "crop_size": crop_size,
+                          "shards": sharded.shards, "cuda_graph": graph,
                           "bit_identical_to_single_gpu": ok,
                           "frames": report}))
     dist.barrier()

@@ -15,13 +15,13 @@ import torch
 from . import ops
 from .exchange import Exchange
 from .tracker import State
-from .vit_weights import VIT_CONFIGS, init_state_dict, pack_for_device
+from .vit_weights import VIT_CONFIGS, init_state_dict, load_checkpoint, pack_for_device
 
 
 class MultiStreamTracker:
     def __init__(self, n_streams, model="vit_base_patch16_224", n_particles=2048, seed=0,
                  device="cuda", tau=0.1, sigma_scale=0.01, state_dict=None, first_stream_id=0,
-                 crop_size=224):
+                 crop_size=224, stream_ids=None):
         if not torch.cuda.is_available():
             raise RuntimeError("MultiStreamTracker needs a CUDA device: there is no CPU fallback")
         self.S, self.n, self.seed, self.tau = int(n_streams), int(n_particles), int(seed), float(tau)
@@ -31,10 +31,15 @@ class MultiStreamTracker:
         self.crop_size = int(crop_size)
         self.n_patch = ops.n_patch(self.crop_size)
         self.sigma_scale = float(np.float32(sigma_scale))
-        self.stream_ids = [first_stream_id + s for s in range(self.S)]
+        # Philox stream ids: global ids when the streams of a job are sharded over several GPUs
+        # (stream s -> rank s mod R), so a stream's trajectory does not depend on where it runs
+        self.stream_ids = ([first_stream_id + s for s in range(self.S)] if stream_ids is None
+                           else [int(s) for s in stream_ids])
+        if len(self.stream_ids) != self.S:
+            raise ValueError("stream_ids must list one id per stream")
         cfg = VIT_CONFIGS[model]
         self.dim = cfg["dim"]
-        sd = state_dict if state_dict is not None else init_state_dict(model)
+        sd = load_checkpoint(state_dict, model) if state_dict is not None else init_state_dict(model)
         self.encoder = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], self.S * self.n,
                                       pack_for_device(model, sd, crop_size=self.crop_size),
                                       device=self.device, crop_size=self.crop_size)

@@ -29,7 +29,7 @@ import torch
 
 from . import ops
 from .exchange import Exchange, shard_range, shard_sizes
-from .vit_weights import VIT_CONFIGS, init_state_dict, pack_for_device
+from .vit_weights import VIT_CONFIGS, init_state_dict, load_checkpoint, pack_for_device
 
 
 class _Stage:
@@ -116,7 +116,8 @@ class Tracker:
         cfg = VIT_CONFIGS[model]
         self.dim = cfg["dim"]
         if encoder is None:
-            sd = state_dict if state_dict is not None else init_state_dict(model)
+            sd = (load_checkpoint(state_dict, model) if state_dict is not None
+                  else init_state_dict(model))
             encoder = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], self.n,
                                      pack_for_device(model, sd, dtype, self.crop_size),
                                      device=self.device, dtype=dtype, crop_size=self.crop_size,

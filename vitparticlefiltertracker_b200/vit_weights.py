@@ -83,6 +83,50 @@ def init_state_dict(model: str, seed: int = WEIGHT_SEED) -> dict:
     return sd
 
 
+def _expected_shapes(model: str) -> dict:
+    c = VIT_CONFIGS[model]
+    d = c["dim"]
+    shapes = {"patch_embed.proj.weight": (d, 3, 16, 16), "patch_embed.proj.bias": (d,),
+              "cls_token": (1, 1, d), "pos_embed": None, "norm.weight": (d,), "norm.bias": (d,)}
+    per_block = [(d,), (d,), (3 * d, d), (3 * d,), (d, d), (d,), (d,), (d,), (4 * d, d), (4 * d,),
+                 (d, 4 * d), (d,)]
+    for i in range(c["depth"]):
+        shapes.update(zip(_block_keys(i), per_block))
+    return shapes
+
+
+def load_checkpoint(src, model: str) -> dict:
+    """A timm `vit_*_patch16_224` checkpoint -> the fp32 state_dict the tracker packs.
+
+    `src`: a path for `torch.load`, or a dict.  Real checkpoints come wrapped
+    (``{"state_dict": ...}`` / ``{"model": ...}``), prefixed (``module.``), with keys the tracker
+    has no use for (``head.*``, ``fc_norm.*``: the likelihood reads the CLS embedding after the
+    final norm, i.e. `num_classes=0, global_pool='token'`) and often in fp16 / bf16: all handled
+    here.  A missing key or a wrong shape raises with the key's name."""
+    sd = torch.load(src, map_location="cpu", weights_only=True) if isinstance(src, (str, bytes)) \
+        or hasattr(src, "__fspath__") else src
+    for k in ("state_dict", "model"):
+        if k in sd and isinstance(sd[k], dict):
+            sd = sd[k]
+    sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+    out = {}
+    for key, shape in _expected_shapes(model).items():
+        if key not in sd:
+            raise KeyError(f"checkpoint has no {key!r} (expected timm {model} key names)")
+        t = torch.as_tensor(sd[key]).detach().to(torch.float32)
+        if key == "pos_embed":
+            g = int(round((t.shape[1] - 1) ** 0.5)) if t.dim() == 3 else 0
+            if t.dim() != 3 or t.shape[0] != 1 or t.shape[2] != VIT_CONFIGS[model]["dim"] \
+                    or g * g + 1 != t.shape[1]:
+                raise ValueError(f"pos_embed has shape {tuple(t.shape)}, need [1, 1+g*g, D]")
+        elif tuple(t.shape) != shape:
+            raise ValueError(f"{key} has shape {tuple(t.shape)}, {model} needs {shape}")
+        if not torch.isfinite(t).all():
+            raise ValueError(f"{key} holds non-finite values")
+        out[key] = t.contiguous()
+    return out
+
+
 def pack_for_device(model: str, sd: dict, dtype=torch.bfloat16, crop_size: int = 224) -> list:
     """timm state_dict -> list of CPU tensors in libvpf pointer order: GEMM weights in the 16-bit
     operand type (`dtype`: bf16 or fp16) [out][in] (the K-major B operand), everything else fp32.
