@@ -15,8 +15,9 @@ e2e    = the same through the public API with HOST frames: pinned host -> device
 roofline = the tcgen05 GEMM family (qkv/proj/fc1/fc2), timed live with CUDA events inside a
          sustained loop, against MEASURED_PEAKS.json's sustained bf16 figure.
 cpu_baseline = the CPU oracle (a port: the upstream repo is a README only) on a bounded sample.
-residual_fp16 = (N=1 only, informative) the headline workload with the encoder's residual stream
-         stored in fp16 instead of fp32 (Tracker(residual_dtype=torch.float16)).
+residual_fp32 / fp16_operands = (N=1 only, informative) the headline workload with the encoder's
+         residual stream stored in fp32 instead of the default fp16, and with fp16 instead of bf16
+         GEMM operands (8x closer to the fp32 oracle, ~5 % slower under the power cap).
 native_resolution = (N=1 only, informative, measured after everything above) the same workload
          at crop size 64 -- SURVEY.md section 8f-2 "native-resolution crops": 17 tokens per
          particle instead of 197, position embedding resampled, oracle revised to match
@@ -47,7 +48,7 @@ PARTICLES_PER_GPU = 4096
 FRAME_HW = (1080, 1920)
 TARGET = (96, 96)
 CLIP_FRAMES = 16
-DEFAULT_RESIDUAL = "fp32"      # storage type of the residual stream in the headline run
+DEFAULT_RESIDUAL = "fp16"      # storage type of the residual stream in the headline run
 DEFAULT_SHARDS = "equal"       # particle split across GPUs in the headline run (N > 1)
 
 

@@ -41,8 +41,8 @@ def main(path="config.yaml"):
                   sigma_init=cfg.get("sigma_init"), state_dict=sd, dtype=dtype,
                   cuda_graph=bool(cfg.get("cuda_graph", False)),
                   crop_size=int(cfg.get("crop_size", 224)),
-                  residual_dtype=torch.float16 if cfg.get("residual_dtype", "fp32") == "fp16"
-                  else torch.float32)
+                  residual_dtype=torch.float32 if cfg.get("residual_dtype", "fp16") == "fp32"
+                  else torch.float16)
     frames = iter(frames)
     trk.init(next(frames), bbox)
     t0 = time.perf_counter()

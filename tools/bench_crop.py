@@ -28,7 +28,7 @@ def main():
     dev = torch.device("cuda")
     g = torch.Generator(device="cpu").manual_seed(0)
     frame = torch.randint(0, 256, (1080, 1920, 3), dtype=torch.uint8, generator=g).to(dev)
-    res = {"kernel": "crop_sep_kernel", "n": n}
+    res = {"kernel": "crop_col_kernel", "n": n}
     for S in (224, 64):
         patches = torch.empty(n * (S // 16) ** 2, 768, dtype=torch.bfloat16, device=dev)
         for box in (48, 96, 160, 224, 400):

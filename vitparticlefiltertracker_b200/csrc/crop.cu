@@ -26,27 +26,29 @@ __device__ __forceinline__ float sample_coord(float base, float step, int k, flo
 }
 
 // ---------------------------------------------------------------------------------------------
-// Separable bilinear.  One CTA = one patch row (16 x S output pixels) of one crop, 7 warps.
-// Bilinear interpolation as the oracle writes it is  val = gy*top + fy*bot  with
-//   top = gx*p[y0][x0] + fx*p[y0][x1],  bot = gx*p[y1][x0] + fx*p[y1][x1]:
-// `top` / `bot` depend only on (source row, output column), and with up-sampling (box smaller than
-// the crop, the tracker's normal case) the 16 output rows of a CTA touch only ~16*h/S + 2 source
-// rows.  So:
-//   phase A  the particle box and the S horizontal taps (x0, frac) -> shared memory
-//   phase B  H[r][c][j] = gx*p[r][x0_j][c] + fx*p[r][x1_j][c] for every touched source row r, once,
-//            in fp32 with the oracle's operation order -> shared memory (<= h_cap rows)
-//   phase C  out[i][j][c] = gy_i*H[y0_i] + fy_i*H[y1_i], normalise, convert: packed fp32x2
-//            products, never-fused scalar sums, 16-byte shared loads, one warp per 16x16 patch
-//            writing three 512-byte runs.
-// Same roundings in the same order as the oracle => still bit-equal to bf16(oracle); about 8
-// instructions per output value instead of the 20 of a per-output four-tap kernel.  Patch rows that
-// touch more than h_cap source rows (down-sampling: no row reuse to exploit) stage the raw source
-// window as bytes instead (coalesced 4-byte loads) and interpolate per output, same arithmetic;
-// windows too large even for that take their taps from global memory.
-static constexpr int kV2Threads = 224;                       // 7 warps: 14 patches in two rounds
-static constexpr int kHRowsMax = 20;                         // largest H-row budget a launch may ask for
-static constexpr int kHPitchMax = 3 * kMaxCrop + 4;          // floats per H row (+4: bank spread)
-static constexpr int kV2SmemMax = kHRowsMax * kHPitchMax * 4;   // 54 080 B (dynamic)
+// Column-owner kernel.  One CTA = one crop; one thread = two adjacent output columns, walked down
+// all S output rows.  Bilinear interpolation as the oracle writes it is
+//   val = gy*top + fy*bot,   top = gx*p[y0][x0] + fx*p[y0][x1],   bot = gx*p[y1][x0] + fx*p[y1][x1].
+// `top` / `bot` depend only on (source row, output column), and y0 is nondecreasing in the output
+// row, so a thread keeps the two horizontally interpolated source rows of its columns in
+// registers and refreshes one only when y0 advances (every S/h rows: ~2.3 output rows per source
+// row for a 96-pixel box).  Everything that is per crop or per row is done ONCE per crop (the round-1
+// kernel, one CTA per patch row, paid box / taps / barriers 14 times per crop and ran at 24
+// instructions per output value, issue-bound at 75 % issue-active -- profiles/ncu_crop_attn_r02.json):
+//   prologue   box -> per-row (y0, fy) table in shared memory; the thread's own (x0, fx) taps in
+//              registers; the crop's source window (<= ~100 x 100 pixels for a 96-pixel target)
+//              staged in shared memory with coalesced aligned 4-byte loads
+//   main loop  per row: 2 table loads, <= 1 row refresh (12 shared byte loads, bytes -> floats with
+//              the 2^23 magic constant instead of I2F, 3 x (2 FMUL2 + FADD2)), 3 x (3 FMUL2 +
+//              2 FADD2 + 1 pack) for six outputs, three 4-byte stores that fill whole 32-byte
+//              sectors of the patch-major output (8 lanes = one 16-pixel patch row = 32 B)
+// All arithmetic keeps the oracle's fp32 operation order with round-to-nearest operations (packed
+// products, scalar never-fused sums: see sum_rn), so the output still equals bf16(oracle) bit for
+// bit.  Windows that do not fit the launch's shared-memory budget (boxes much
+// larger than the nominal target, down-sampling) read their taps from global memory instead: same
+// arithmetic, same result, slower.
+static constexpr int kColThreads = 128;                      // 2 columns per thread, S/2 <= 112 active
+static constexpr int kWinWordsMax = 24 * 1024;               // 96 KB: largest window a launch may ask for
 
 __device__ __forceinline__ float2 fmul2_rn(float2 a, float2 b) {
   unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
@@ -55,30 +57,65 @@ __device__ __forceinline__ float2 fmul2_rn(float2 a, float2 b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
   return *reinterpret_cast<float2*>(&rd);
 }
-// Two outputs: products packed (FMUL2), sums with the scalar never-fused intrinsic.  (ptxas
-// contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 -- checked in the SASS -- which would change
-// the oracle's roundings; __fadd_rn is documented never to be merged into an FMA.)
+__device__ __forceinline__ float2 fadd2_rn(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+// two bytes (0..255) -> two floats, exactly: 0x4B000000 | b is the float 2^23 + b
+__device__ __forceinline__ float2 bytes2f(uint32_t a, uint32_t b) {
+  return fadd2_rn(make_float2(__uint_as_float(0x4B000000u | a), __uint_as_float(0x4B000000u | b)),
+                  make_float2(-8388608.0f, -8388608.0f));
+}
+// Sum of two packed products, each rounded on its own: products packed (FMUL2), sums with the
+// scalar never-fused intrinsic.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 -- checked
+// in the SASS, with and without -fmad=false -- which would skip the oracle's rounding of the
+// product; __fadd_rn is documented never to be merged into an FMA.
+__device__ __forceinline__ float2 sum_rn(float2 a, float2 b) {
+  return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+}
+// two outputs of one channel: gy*top + fy*bot, then (v * 2/255) - 1, packed to 16 bits
 __device__ __forceinline__ uint32_t blend2(float2 gy2, float2 fy2, float2 top, float2 bot, bool f16) {
-  const float2 t0 = fmul2_rn(gy2, top), t1 = fmul2_rn(fy2, bot);
-  const float2 val = make_float2(__fadd_rn(t0.x, t1.x), __fadd_rn(t0.y, t1.y));
+  const float2 val = sum_rn(fmul2_rn(gy2, top), fmul2_rn(fy2, bot));
   const float2 nn = fmul2_rn(val, make_float2(2.0f / 255.0f, 2.0f / 255.0f));
   return pack16x2(__fadd_rn(nn.x, -1.0f), __fadd_rn(nn.y, -1.0f), f16);
 }
 
+// Horizontally interpolated source row for the thread's two columns, three channels:
+//   h[c] = gx * p[x0][c] + fx * p[x1][c]     (.x = column A, .y = column B)
+// `row` points at pixel 0 of the source row (inside the shared window or in global memory).
+template <bool kShared>
+__device__ __forceinline__ void load_h(const uint8_t* row, int oa0, int oa1, int ob0, int ob1,
+                                       float2 gx2, float2 fx2, float2 (&h)[3]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    uint32_t a0, a1, b0, b1;
+    if (kShared) {
+      a0 = row[oa0 + c]; a1 = row[oa1 + c]; b0 = row[ob0 + c]; b1 = row[ob1 + c];
+    } else {
+      a0 = __ldg(row + oa0 + c); a1 = __ldg(row + oa1 + c);
+      b0 = __ldg(row + ob0 + c); b1 = __ldg(row + ob1 + c);
+    }
+    h[c] = sum_rn(fmul2_rn(gx2, bytes2f(a0, b0)), fmul2_rn(fx2, bytes2f(a1, b1)));
+  }
+}
+
 template <bool kFromState>
-__global__ void __launch_bounds__(kV2Threads) crop_sep_kernel(const uint8_t* __restrict__ frame,
-                                                              int H, int W,
-                                                              const float* __restrict__ src, int n,
-                                                              int ld, float w0, float h0,
-                                                              __nv_bfloat16* __restrict__ out,
-                                                              bool f16, int S, int h_cap, int smem_words) {
-  extern __shared__ __align__(16) float s_h[];               // [h_cap][3][S] (+4 floats per row)
-  __shared__ float s_fx[kMaxCrop];
-  __shared__ int s_x0[kMaxCrop];
+__global__ void __launch_bounds__(kColThreads) crop_col_kernel(const uint8_t* __restrict__ frame,
+                                                               int H, int W,
+                                                               const float* __restrict__ src, int n,
+                                                               int ld, float w0, float h0,
+                                                               __nv_bfloat16* __restrict__ out,
+                                                               bool f16, int S, int win_words) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];           // [S] y0 | [S] fy | window words
+  int* s_y0 = reinterpret_cast<int*>(s_dyn);
+  float* s_fy = reinterpret_cast<float*>(s_dyn) + S;
+  uint32_t* s_win = reinterpret_cast<uint32_t*>(s_dyn) + 2 * S;
   pdl_launch_dependents();
+  const int crop = blockIdx.x, tid = threadIdx.x;
   const int grid_p = S / kPatch;
-  const int crop = blockIdx.x, py = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   pdl_wait();                                                // the particle state is the motion kernel's output
   Box b;
   if (kFromState) {
@@ -95,54 +132,31 @@ __global__ void __launch_bounds__(kV2Threads) crop_sep_kernel(const uint8_t* __r
   const float basex = __fsub_rn(__fsub_rn(b.cx, __fmul_rn(0.5f, b.w)), 0.5f);
   const float basey = __fsub_rn(__fsub_rn(b.cy, __fmul_rn(0.5f, b.h)), 0.5f);
   const float xmax = (float)(W - 1), ymax = (float)(H - 1);
-  const int i0 = py * kPatch;
 
-  // ---- phase A: horizontal taps ----
-  if (threadIdx.x < S) {
-    const float xs = sample_coord(basex, stepx, threadIdx.x, xmax);
-    const float x0f = floorf(xs);
-    s_fx[threadIdx.x] = __fsub_rn(xs, x0f);
-    s_x0[threadIdx.x] = (int)x0f;
+  // ---- per-row table: source row and vertical fraction of every output row ----
+  for (int i = tid; i < S; i += kColThreads) {
+    const float ys = sample_coord(basey, stepy, i, ymax);
+    const float y0f = floorf(ys);
+    s_y0[i] = (int)y0f;
+    s_fy[i] = __fsub_rn(ys, y0f);
   }
-  // source rows this patch row touches (sample coordinates are monotone in the output index)
-  const int y_lo = (int)floorf(sample_coord(basey, stepy, i0, ymax));
-  const int y_hi = min((int)floorf(sample_coord(basey, stepy, i0 + kPatch - 1, ymax)) + 1, H - 1);
+  // ---- source window of the crop (sample coordinates are monotone in the output index when the
+  // box size is positive; anything else reads global memory) ----
+  const int x_lo = (int)floorf(sample_coord(basex, stepx, 0, xmax));
+  const int x_hi = min((int)floorf(sample_coord(basex, stepx, S - 1, xmax)) + 1, W - 1);
+  const int y_lo = (int)floorf(sample_coord(basey, stepy, 0, ymax));
+  const int y_hi = min((int)floorf(sample_coord(basey, stepy, S - 1, ymax)) + 1, H - 1);
   const int rows = y_hi - y_lo + 1;
-  const int pitch = 3 * S + 4;
-  // 0: separable (H rows fit);  1: raw source window staged as bytes (down-sampling: no row is
-  // reused, so interpolate per output from shared memory);  2: window too large, global taps
-  int mode = rows <= h_cap ? 0 : 2;
-  int x_lo = 0, wpitch = 0;
-  if (mode == 2) {
-    x_lo = (int)floorf(sample_coord(basex, stepx, 0, xmax));
-    const int x_hi = min((int)floorf(sample_coord(basex, stepx, S - 1, xmax)) + 1, W - 1);
-    wpitch = ((x_hi - x_lo + 1) * 3 + 6) / 4 + 1;              // words per staged row
-    if (rows * wpitch <= smem_words) mode = 1;
-  }
-  __syncthreads();
-
-  if (mode == 0) {
-    // ---- phase B: horizontally interpolated source rows ----
-    for (int idx = threadIdx.x; idx < rows * S; idx += blockDim.x) {
-      const int r = idx / S, j = idx - r * S;
-      const float fx = s_fx[j];
-      const float gx = __fsub_rn(1.0f, fx);
-      const int x0 = s_x0[j], x1 = min(x0 + 1, W - 1);
-      const uint8_t* row = frame + (size_t)(y_lo + r) * W * 3;
-      float* h = s_h + r * pitch + j;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float p0 = (float)__ldg(row + x0 * 3 + c), p1 = (float)__ldg(row + x1 * 3 + c);
-        h[c * S] = __fadd_rn(__fmul_rn(gx, p0), __fmul_rn(fx, p1));
-      }
-    }
-  } else if (mode == 1) {
-    // ---- raw window, 4-byte aligned words (coalesced) ----
-    uint32_t* stage = reinterpret_cast<uint32_t*>(s_h);
-    const uintptr_t end = reinterpret_cast<uintptr_t>(frame) + (size_t)H * W * 3;
-    for (int idx = threadIdx.x; idx < rows * wpitch; idx += blockDim.x) {
+  const int wpitch = ((x_hi - x_lo + 1) * 3 + 6) / 4 + 1;    // 4-byte words per staged row
+  const bool use_win = stepx >= 0.0f && stepy >= 0.0f && rows > 0 && x_hi >= x_lo &&
+                       (long long)rows * wpitch <= (long long)win_words;
+  const uintptr_t f0 = reinterpret_cast<uintptr_t>(frame);
+  if (use_win) {
+    // a staged row starts at the 4-byte aligned address at or below its first pixel
+    const uintptr_t end = f0 + (size_t)H * W * 3;
+    for (int idx = tid; idx < rows * wpitch; idx += kColThreads) {
       const int r = idx / wpitch, wd = idx - r * wpitch;
-      const uintptr_t g0 = reinterpret_cast<uintptr_t>(frame) + ((size_t)(y_lo + r) * W + x_lo) * 3;
+      const uintptr_t g0 = f0 + ((size_t)(y_lo + r) * W + x_lo) * 3;
       const uintptr_t ga = (g0 & ~(uintptr_t)3) + (uintptr_t)wd * 4;
       uint32_t v = 0;
       if (ga + 4 <= end) {
@@ -151,71 +165,62 @@ __global__ void __launch_bounds__(kV2Threads) crop_sep_kernel(const uint8_t* __r
         for (int k = 0; k < 4; ++k)
           if (ga + k < end) v |= (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(ga + k)) << (8 * k);
       }
-      stage[idx] = v;
+      s_win[idx] = v;
     }
   }
   __syncthreads();
+  if (2 * tid >= S) return;
 
-  // ---- phase C: vertical blend, normalise, convert, store (one warp per patch) ----
-  const int ky = lane >> 1, kx0 = (lane & 1) * 8;
-  const int i = i0 + ky;
-  const float ys = sample_coord(basey, stepy, i, ymax);
-  const float y0f = floorf(ys);
-  const float fy = __fsub_rn(ys, y0f);
-  const float gy = __fsub_rn(1.0f, fy);
-  const int y0 = (int)y0f, y1 = min(y0 + 1, H - 1);
-  const float2 gy2 = make_float2(gy, gy), fy2 = make_float2(fy, fy);
-  for (int px = warp; px < grid_p; px += (int)(blockDim.x >> 5)) {
-    const int j0 = px * kPatch + kx0;
-    __nv_bfloat16* dst = out + ((size_t)crop * grid_p * grid_p + py * grid_p + px) * kPatchK +
-                         ky * kPatch + kx0;
-    if (mode == 0) {
-      const float* h0p = s_h + (y0 - y_lo) * pitch + j0;
-      const float* h1p = s_h + (y1 - y_lo) * pitch + j0;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        uint4 o;
-        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const float4 t = *reinterpret_cast<const float4*>(h0p + c * S + q * 4);
-          const float4 u = *reinterpret_cast<const float4*>(h1p + c * S + q * 4);
-          ow[q * 2 + 0] = blend2(gy2, fy2, make_float2(t.x, t.y), make_float2(u.x, u.y), f16);
-          ow[q * 2 + 1] = blend2(gy2, fy2, make_float2(t.z, t.w), make_float2(u.z, u.w), f16);
-        }
-        *reinterpret_cast<uint4*>(dst + c * 256) = o;
+  // ---- the thread's two columns: horizontal taps in registers ----
+  const int ja = 2 * tid;
+  const float xsa = sample_coord(basex, stepx, ja, xmax), xsb = sample_coord(basex, stepx, ja + 1, xmax);
+  const float xa0f = floorf(xsa), xb0f = floorf(xsb);
+  const float2 fx2 = make_float2(__fsub_rn(xsa, xa0f), __fsub_rn(xsb, xb0f));
+  const float2 gx2 = make_float2(__fsub_rn(1.0f, fx2.x), __fsub_rn(1.0f, fx2.y));
+  const int xa0 = (int)xa0f, xb0 = (int)xb0f;
+  const int oa0 = xa0 * 3, oa1 = min(xa0 + 1, W - 1) * 3, ob0 = xb0 * 3, ob1 = min(xb0 + 1, W - 1) * 3;
+  const int px = ja >> 4, kx = ja & 15;
+  uint8_t* dst = reinterpret_cast<uint8_t*>(out) +
+                 (((size_t)crop * grid_p * grid_p + px) * kPatchK + kx) * 2;
+  const uint8_t* wbase = reinterpret_cast<const uint8_t*>(s_win);
+  // address of pixel 0 of source row y: inside the window, row (y - y_lo) starts at the aligned
+  // word at or below its first pixel x_lo, i.e. `shift` bytes before it
+  auto win_row = [&](int y) {
+    const int shift = (int)((f0 + ((size_t)y * W + x_lo) * 3) & 3);
+    return wbase + (size_t)(y - y_lo) * wpitch * 4 + shift - x_lo * 3;
+  };
+  auto refresh = [&](int y, float2 (&h)[3]) {
+    if (use_win) load_h<true>(win_row(y), oa0, oa1, ob0, ob1, gx2, fx2, h);
+    else load_h<false>(frame + (size_t)y * W * 3, oa0, oa1, ob0, ob1, gx2, fx2, h);
+  };
+
+  float2 ht[3], hb[3];                                       // interpolated rows top_y / bot_y
+  int top_y = -1, bot_y = -1;
+#pragma unroll 1
+  for (int py = 0; py < grid_p; ++py) {
+    uint8_t* drow = dst + (size_t)py * grid_p * kPatchK * 2;
+#pragma unroll 4
+    for (int ky = 0; ky < kPatch; ++ky) {
+      const int i = py * kPatch + ky;
+      const int y0 = s_y0[i];
+      const float fy = s_fy[i];
+      const float gy = __fsub_rn(1.0f, fy);
+      const int y1 = min(y0 + 1, H - 1);
+      if (y0 != top_y) {                                     // CTA-uniform branches
+        if (y0 == bot_y) { ht[0] = hb[0]; ht[1] = hb[1]; ht[2] = hb[2]; }
+        else refresh(y0, ht);
+        top_y = y0;
       }
-    } else {
-      // four taps per output value (from the staged window or from global), identical arithmetic
-      const uint8_t* tap = frame;
-      long long off0 = (long long)y0 * W * 3, off1 = (long long)y1 * W * 3;
-      if (mode == 1) {
-        // a staged row starts at the 4-byte aligned address at or below its first pixel (x_lo)
-        tap = reinterpret_cast<const uint8_t*>(s_h);
-        const int sh0 = (int)((reinterpret_cast<uintptr_t>(frame) + ((size_t)y0 * W + x_lo) * 3) & 3);
-        const int sh1 = (int)((reinterpret_cast<uintptr_t>(frame) + ((size_t)y1 * W + x_lo) * 3) & 3);
-        off0 = (long long)(y0 - y_lo) * wpitch * 4 + sh0 - x_lo * 3;
-        off1 = (long long)(y1 - y_lo) * wpitch * 4 + sh1 - x_lo * 3;
+      if (y1 != bot_y) {
+        if (y1 == top_y) { hb[0] = ht[0]; hb[1] = ht[1]; hb[2] = ht[2]; }
+        else refresh(y1, hb);
+        bot_y = y1;
       }
-      __align__(16) uint16_t v[3][8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float fx = s_fx[j0 + e];
-        const int x0 = s_x0[j0 + e], x1 = min(x0 + 1, W - 1);
-        const float gx = __fsub_rn(1.0f, fx);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float p00 = (float)tap[off0 + x0 * 3 + c], p01 = (float)tap[off0 + x1 * 3 + c];
-          const float p10 = (float)tap[off1 + x0 * 3 + c], p11 = (float)tap[off1 + x1 * 3 + c];
-          const float top = __fadd_rn(__fmul_rn(gx, p00), __fmul_rn(fx, p01));
-          const float bot = __fadd_rn(__fmul_rn(gx, p10), __fmul_rn(fx, p11));
-          const float val = __fadd_rn(__fmul_rn(gy, top), __fmul_rn(fy, bot));
-          v[c][e] = pack16(__fsub_rn(__fmul_rn(val, 2.0f / 255.0f), 1.0f), f16);
-        }
-      }
+      const float2 gy2 = make_float2(gy, gy), fy2 = make_float2(fy, fy);
 #pragma unroll
       for (int c = 0; c < 3; ++c)
-        *reinterpret_cast<uint4*>(dst + c * 256) = *reinterpret_cast<const uint4*>(v[c]);
+        *reinterpret_cast<uint32_t*>(drow + (c * 256 + ky * kPatch) * 2) =
+            blend2(gy2, fy2, ht[c], hb[c], f16);
     }
   }
 }
@@ -223,42 +228,29 @@ __global__ void __launch_bounds__(kV2Threads) crop_sep_kernel(const uint8_t* __r
 template <bool kFromState>
 static int launch_crop(const uint8_t* frame, int H, int W, const float* src, int n, int ld, float w0,
                        float h0, void* out, bool f16, int S, cudaStream_t stream) {
-  {
-    static bool attr[32] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr[dev & 31]) {
-      VPF_CUDA(cudaFuncSetAttribute(crop_sep_kernel<kFromState>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kV2SmemMax));
-      attr[dev & 31] = true;
-    }
-    // H-row budget per CTA: what a box of the nominal height needs (16*h/S + 2 source rows per
-    // patch row) with 40 % head-room for the scale state, so that small boxes leave shared memory
-    // for more resident CTAs; explicit boxes (height unknown on the host) get the maximum.
-    // Down-sampling boxes (no H-row reuse) get room for the raw byte window instead.
-    int h_cap = kHRowsMax;
-    int smem = h_cap * (3 * S + 4) * 4;
-    if (kFromState) {
-      const float rows_f = 16.0f * h0 * 1.4f / (float)S + 3.0f;
-      h_cap = rows_f < 6.f ? 6 : (rows_f > (float)kHRowsMax ? kHRowsMax : (int)rows_f);
-      smem = h_cap * (3 * S + 4) * 4;
-      if (rows_f > (float)kHRowsMax) {
-        const float raw = rows_f * (w0 * 1.4f * 3.0f + 16.0f);
-        smem = raw > (float)kV2SmemMax ? kV2SmemMax : (raw > (float)smem ? (int)raw : smem);
-      }
-    } else if (S < kMaxCrop) {
-      smem = kV2SmemMax;           // explicit boxes: box size unknown on the host
-    }
-    smem = (smem + 15) & ~15;
-    // one warp per two patches (S = 224 -> 7 warps); when the raw window is staged instead, every
-    // thread helps with the copy
-    int warps = (S / kPatch + 1) / 2 < 2 ? 2 : (S / kPatch + 1) / 2;
-    if (smem > h_cap * (3 * S + 4) * 4 || !kFromState) warps = kV2Threads / 32;
-    VPF_CUDA(launch_pdl(pdl_for_rows((long long)n * (S / kPatch) * (S / kPatch)),
-                        crop_sep_kernel<kFromState>, dim3(n, S / kPatch), dim3(warps * 32),
-                        (size_t)smem, stream, frame, H, W, src, n, ld, w0, h0,
-                        (__nv_bfloat16*)out, f16, S, h_cap, smem / 4));
+  static bool attr[32] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr[dev & 31]) {
+    VPF_CUDA(cudaFuncSetAttribute(crop_col_kernel<kFromState>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  2 * kMaxCrop * 4 + kWinWordsMax * 4));
+    attr[dev & 31] = true;
   }
+  // Window budget per CTA: what a box of the nominal size needs, with 15 % head-room for the scale
+  // state (a particle whose window outgrows it reads global memory instead: correct, slower), so
+  // that small targets leave shared memory for more resident CTAs.  Explicit boxes (size unknown
+  // on the host; one launch per tracker init) get the maximum.
+  int win_words = kWinWordsMax;
+  if (kFromState) {
+    const float rows_f = h0 * 1.15f + 4.0f, words_f = (w0 * 1.15f + 4.0f) * 0.75f + 3.0f;
+    const float need = rows_f * words_f;
+    win_words = need > (float)kWinWordsMax ? kWinWordsMax : (need < 1024.f ? 1024 : (int)need);
+  }
+  const size_t smem = (size_t)2 * S * 4 + (size_t)win_words * 4;
+  VPF_CUDA(launch_pdl(pdl_for_rows((long long)n * (S / kPatch) * (S / kPatch)),
+                      crop_col_kernel<kFromState>, dim3(n), dim3(kColThreads), smem, stream, frame,
+                      H, W, src, n, ld, w0, h0, (__nv_bfloat16*)out, f16, S, win_words));
   return VPF_OK;
 }
 

@@ -21,7 +21,7 @@ from .vit_weights import VIT_CONFIGS, init_state_dict, load_checkpoint, pack_for
 class MultiStreamTracker:
     def __init__(self, n_streams, model="vit_base_patch16_224", n_particles=2048, seed=0,
                  device="cuda", tau=0.1, sigma_scale=0.01, state_dict=None, first_stream_id=0,
-                 crop_size=224, stream_ids=None):
+                 crop_size=224, stream_ids=None, residual_dtype=torch.float16):
         if not torch.cuda.is_available():
             raise RuntimeError("MultiStreamTracker needs a CUDA device: there is no CPU fallback")
         self.S, self.n, self.seed, self.tau = int(n_streams), int(n_particles), int(seed), float(tau)
@@ -42,7 +42,8 @@ class MultiStreamTracker:
         sd = load_checkpoint(state_dict, model) if state_dict is not None else init_state_dict(model)
         self.encoder = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], self.S * self.n,
                                       pack_for_device(model, sd, crop_size=self.crop_size),
-                                      device=self.device, crop_size=self.crop_size)
+                                      device=self.device, crop_size=self.crop_size,
+                                      residual_dtype=residual_dtype)
         dev, S, n = self.device, self.S, self.n
         f32 = torch.float32
         self.particles = torch.zeros((S, 6, n), dtype=f32, device=dev)

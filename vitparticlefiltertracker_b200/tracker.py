@@ -76,7 +76,7 @@ class Tracker:
     def __init__(self, model="vit_base_patch16_224", n_particles=4096, seed=0, device="cuda",
                  dtype=torch.bfloat16, tau=0.1, sigma_pos=None, sigma_vel=None, sigma_scale=0.01,
                  sigma_init=None, state_dict=None, process_group=None, stream_id=0,
-                 encoder=None, cuda_graph=False, crop_size=224, residual_dtype=torch.float32,
+                 encoder=None, cuda_graph=False, crop_size=224, residual_dtype=torch.float16,
                  shards=None):
         if not torch.cuda.is_available():
             raise RuntimeError("Tracker needs a CUDA device: the hot path has no CPU fallback")
@@ -84,6 +84,12 @@ class Tracker:
             raise ValueError("the sm_100a ViT path takes bf16 (default) or fp16 operands, "
                              "fp32 accumulation")
         self.dtype = dtype
+        # Storage type of the encoder's residual stream.  fp16 (default since round 2; saturating
+        # conversion, arithmetic stays fp32) halves the residual bytes -- 35 % of a block's HBM
+        # traffic -- for -5 % time per frame, and stays inside the stated bf16 tolerance
+        # (profiles/parity_r02.json: it adds ~2 % to the bf16 operands' own distance from the
+        # oracle).  torch.float32 restores the round-1 behaviour.
+        self.residual_dtype = residual_dtype
         # 224 = the oracle's default; a smaller multiple of 16 is the "native-resolution crops"
         # option of SURVEY.md section 8f-2 (e.g. 64 -> 17 tokens per particle instead of 197)
         self.crop_size = int(crop_size)
