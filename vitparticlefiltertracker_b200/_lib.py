@@ -70,7 +70,9 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB
+    """libvpf.so of this tree; VPF_LIB_PATH points at another build of the same ABI (same-box A/B
+    runs of two kernel versions: tools/ab_bench.sh)."""
+    return os.environ.get("VPF_LIB_PATH") or _build.LIB
 
 
 def load(build_if_missing: bool = True):
@@ -79,7 +81,7 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = lib_path()
-    if build_if_missing and (not os.path.exists(path) or _build.needs_build()):
+    if build_if_missing and path == _build.LIB and (not os.path.exists(path) or _build.needs_build()):
         _build.build()
     if not os.path.exists(path):
         raise RuntimeError(f"{path} not found: the CUDA extension is required (no CPU fallback)")

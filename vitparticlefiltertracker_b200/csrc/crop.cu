@@ -36,8 +36,9 @@ __device__ __forceinline__ float sample_coord(float base, float step, int k, flo
 // kernel, one CTA per patch row, paid box / taps / barriers 14 times per crop and ran at 24
 // instructions per output value, issue-bound at 75 % issue-active -- profiles/ncu_crop_attn_r02.json):
 //   prologue   box -> per-row (y0, fy) table in shared memory; the thread's own (x0, fx) taps in
-//              registers; the crop's source window (<= ~100 x 100 pixels for a 96-pixel target)
-//              staged in shared memory with coalesced aligned 4-byte loads
+//              registers; the crop's source window (~100 x 100 pixels for a 96-pixel target)
+//              staged in shared memory with coalesced aligned 4-byte loads -- in one piece when
+//              it fits the launch's budget, else in bands of a few patch rows
 //   main loop  per row: 2 table loads, <= 1 row refresh (12 shared byte loads, bytes -> floats with
 //              the 2^23 magic constant instead of I2F, 3 x (2 FMUL2 + FADD2)), 3 x (3 FMUL2 +
 //              2 FADD2 + 1 pack) for six outputs, three 4-byte stores that fill whole 32-byte
@@ -134,45 +135,23 @@ __global__ void __launch_bounds__(kColThreads) crop_col_kernel(const uint8_t* __
   const float xmax = (float)(W - 1), ymax = (float)(H - 1);
 
   // ---- per-row table: source row and vertical fraction of every output row ----
-  for (int i = tid; i < S; i += kColThreads) {
+  for (int i = tid; i < S; i += (int)blockDim.x) {
     const float ys = sample_coord(basey, stepy, i, ymax);
     const float y0f = floorf(ys);
     s_y0[i] = (int)y0f;
     s_fy[i] = __fsub_rn(ys, y0f);
   }
-  // ---- source window of the crop (sample coordinates are monotone in the output index when the
-  // box size is positive; anything else reads global memory) ----
+  // ---- horizontal extent of the crop's source window (sample coordinates are monotone in the
+  // output index when the box size is positive; anything else reads global memory) ----
   const int x_lo = (int)floorf(sample_coord(basex, stepx, 0, xmax));
   const int x_hi = min((int)floorf(sample_coord(basex, stepx, S - 1, xmax)) + 1, W - 1);
-  const int y_lo = (int)floorf(sample_coord(basey, stepy, 0, ymax));
-  const int y_hi = min((int)floorf(sample_coord(basey, stepy, S - 1, ymax)) + 1, H - 1);
-  const int rows = y_hi - y_lo + 1;
   const int wpitch = ((x_hi - x_lo + 1) * 3 + 6) / 4 + 1;    // 4-byte words per staged row
-  const bool use_win = stepx >= 0.0f && stepy >= 0.0f && rows > 0 && x_hi >= x_lo &&
-                       (long long)rows * wpitch <= (long long)win_words;
+  const bool mono = stepx >= 0.0f && stepy >= 0.0f && x_hi >= x_lo;
   const uintptr_t f0 = reinterpret_cast<uintptr_t>(frame);
-  if (use_win) {
-    // a staged row starts at the 4-byte aligned address at or below its first pixel
-    const uintptr_t end = f0 + (size_t)H * W * 3;
-    for (int idx = tid; idx < rows * wpitch; idx += kColThreads) {
-      const int r = idx / wpitch, wd = idx - r * wpitch;
-      const uintptr_t g0 = f0 + ((size_t)(y_lo + r) * W + x_lo) * 3;
-      const uintptr_t ga = (g0 & ~(uintptr_t)3) + (uintptr_t)wd * 4;
-      uint32_t v = 0;
-      if (ga + 4 <= end) {
-        v = __ldg(reinterpret_cast<const uint32_t*>(ga));
-      } else {
-        for (int k = 0; k < 4; ++k)
-          if (ga + k < end) v |= (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(ga + k)) << (8 * k);
-      }
-      s_win[idx] = v;
-    }
-  }
-  __syncthreads();
-  if (2 * tid >= S) return;
 
   // ---- the thread's two columns: horizontal taps in registers ----
-  const int ja = 2 * tid;
+  const bool active = 2 * tid < S;
+  const int ja = active ? 2 * tid : 0;
   const float xsa = sample_coord(basex, stepx, ja, xmax), xsb = sample_coord(basex, stepx, ja + 1, xmax);
   const float xa0f = floorf(xsa), xb0f = floorf(xsb);
   const float2 fx2 = make_float2(__fsub_rn(xsa, xa0f), __fsub_rn(xsb, xb0f));
@@ -183,45 +162,91 @@ __global__ void __launch_bounds__(kColThreads) crop_col_kernel(const uint8_t* __
   uint8_t* dst = reinterpret_cast<uint8_t*>(out) +
                  (((size_t)crop * grid_p * grid_p + px) * kPatchK + kx) * 2;
   const uint8_t* wbase = reinterpret_cast<const uint8_t*>(s_win);
-  // address of pixel 0 of source row y: inside the window, row (y - y_lo) starts at the aligned
-  // word at or below its first pixel x_lo, i.e. `shift` bytes before it
-  auto win_row = [&](int y) {
-    const int shift = (int)((f0 + ((size_t)y * W + x_lo) * 3) & 3);
-    return wbase + (size_t)(y - y_lo) * wpitch * 4 + shift - x_lo * 3;
-  };
-  auto refresh = [&](int y, float2 (&h)[3]) {
-    if (use_win) load_h<true>(win_row(y), oa0, oa1, ob0, ob1, gx2, fx2, h);
-    else load_h<false>(frame + (size_t)y * W * 3, oa0, oa1, ob0, ob1, gx2, fx2, h);
-  };
 
   float2 ht[3], hb[3];                                       // interpolated rows top_y / bot_y
   int top_y = -1, bot_y = -1;
+  __syncthreads();                                           // the row table is complete
+
+  // ---- bands: as many patch rows as the window budget holds source rows for (the whole crop for
+  // a box of the nominal size; a few patch rows for larger boxes, so shared memory per CTA -- and
+  // with it the number of resident CTAs -- does not depend on the box) ----
+  int py = 0;
 #pragma unroll 1
-  for (int py = 0; py < grid_p; ++py) {
-    uint8_t* drow = dst + (size_t)py * grid_p * kPatchK * 2;
-#pragma unroll 4
-    for (int ky = 0; ky < kPatch; ++ky) {
-      const int i = py * kPatch + ky;
-      const int y0 = s_y0[i];
-      const float fy = s_fy[i];
-      const float gy = __fsub_rn(1.0f, fy);
-      const int y1 = min(y0 + 1, H - 1);
-      if (y0 != top_y) {                                     // CTA-uniform branches
-        if (y0 == bot_y) { ht[0] = hb[0]; ht[1] = hb[1]; ht[2] = hb[2]; }
-        else refresh(y0, ht);
-        top_y = y0;
+  while (py < grid_p) {
+    // grow the band while its source rows fit
+    const int y_lo = s_y0[py * kPatch];
+    int band = 0, y_hi = y_lo;
+    if (mono) {
+      while (py + band < grid_p) {
+        const int yh = min(s_y0[(py + band) * kPatch + kPatch - 1] + 1, H - 1);
+        if ((long long)(yh - y_lo + 1) * wpitch > (long long)win_words) break;
+        y_hi = yh;
+        ++band;
       }
-      if (y1 != bot_y) {
-        if (y1 == top_y) { hb[0] = ht[0]; hb[1] = ht[1]; hb[2] = ht[2]; }
-        else refresh(y1, hb);
-        bot_y = y1;
-      }
-      const float2 gy2 = make_float2(gy, gy), fy2 = make_float2(fy, fy);
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-        *reinterpret_cast<uint32_t*>(drow + (c * 256 + ky * kPatch) * 2) =
-            blend2(gy2, fy2, ht[c], hb[c], f16);
     }
+    const bool use_win = band > 0;
+    if (!use_win) band = 1;                                  // this patch row reads global memory
+    if (use_win) {
+      // a staged row starts at the 4-byte aligned address at or below its first pixel
+      const int rows = y_hi - y_lo + 1;
+      const uintptr_t end = f0 + (size_t)H * W * 3;
+      for (int idx = tid; idx < rows * wpitch; idx += (int)blockDim.x) {
+        const int r = idx / wpitch, wd = idx - r * wpitch;
+        const uintptr_t g0 = f0 + ((size_t)(y_lo + r) * W + x_lo) * 3;
+        const uintptr_t ga = (g0 & ~(uintptr_t)3) + (uintptr_t)wd * 4;
+        uint32_t v = 0;
+        if (ga + 4 <= end) {
+          v = __ldg(reinterpret_cast<const uint32_t*>(ga));
+        } else {
+          for (int k = 0; k < 4; ++k)
+            if (ga + k < end) v |= (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(ga + k)) << (8 * k);
+        }
+        s_win[idx] = v;
+      }
+      __syncthreads();
+    }
+    // address of pixel 0 of source row y: inside the window, row (y - y_lo) starts at the aligned
+    // word at or below its first pixel x_lo, i.e. `shift` bytes before it
+    auto refresh = [&](int y, float2 (&h)[3]) {
+      if (use_win) {
+        const int shift = (int)((f0 + ((size_t)y * W + x_lo) * 3) & 3);
+        load_h<true>(wbase + (size_t)(y - y_lo) * wpitch * 4 + shift - x_lo * 3, oa0, oa1, ob0, ob1,
+                     gx2, fx2, h);
+      } else {
+        load_h<false>(frame + (size_t)y * W * 3, oa0, oa1, ob0, ob1, gx2, fx2, h);
+      }
+    };
+    if (active) {
+#pragma unroll 1
+      for (int pr = py; pr < py + band; ++pr) {
+        uint8_t* drow = dst + (size_t)pr * grid_p * kPatchK * 2;
+#pragma unroll 4
+        for (int ky = 0; ky < kPatch; ++ky) {
+          const int i = pr * kPatch + ky;
+          const int y0 = s_y0[i];
+          const float fy = s_fy[i];
+          const float gy = __fsub_rn(1.0f, fy);
+          const int y1 = min(y0 + 1, H - 1);
+          if (y0 != top_y) {                                 // CTA-uniform branches
+            if (y0 == bot_y) { ht[0] = hb[0]; ht[1] = hb[1]; ht[2] = hb[2]; }
+            else refresh(y0, ht);
+            top_y = y0;
+          }
+          if (y1 != bot_y) {
+            if (y1 == top_y) { hb[0] = ht[0]; hb[1] = ht[1]; hb[2] = ht[2]; }
+            else refresh(y1, hb);
+            bot_y = y1;
+          }
+          const float2 gy2 = make_float2(gy, gy), fy2 = make_float2(fy, fy);
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            *reinterpret_cast<uint32_t*>(drow + (c * 256 + ky * kPatch) * 2) =
+                blend2(gy2, fy2, ht[c], hb[c], f16);
+        }
+      }
+    }
+    py += band;
+    if (py < grid_p) __syncthreads();                        // the window is restaged for the next band
   }
 }
 
@@ -237,19 +262,23 @@ static int launch_crop(const uint8_t* frame, int H, int W, const float* src, int
                                   2 * kMaxCrop * 4 + kWinWordsMax * 4));
     attr[dev & 31] = true;
   }
-  // Window budget per CTA: what a box of the nominal size needs, with 15 % head-room for the scale
-  // state (a particle whose window outgrows it reads global memory instead: correct, slower), so
-  // that small targets leave shared memory for more resident CTAs.  Explicit boxes (size unknown
-  // on the host; one launch per tracker init) get the maximum.
-  int win_words = kWinWordsMax;
+  // One warp per 64 output columns.  Window budget per CTA: what a box of the nominal size needs in
+  // one piece, with 15 % head-room for the scale state, capped so that ~16 warps stay resident
+  // per SM whatever the box and the crop size (larger windows are staged in bands of patch rows).
+  // Explicit boxes (size unknown on the host; one launch per tracker init) get the cap.
+  const int warps = (S + 63) / 64;
+  const int ctas_per_sm = (16 + warps - 1) / warps;
+  int cap = (227 * 1024 / ctas_per_sm - 1024 - 2 * S * 4) / 4;
+  if (cap > kWinWordsMax) cap = kWinWordsMax;
+  int win_words = cap;
   if (kFromState) {
     const float rows_f = h0 * 1.15f + 4.0f, words_f = (w0 * 1.15f + 4.0f) * 0.75f + 3.0f;
     const float need = rows_f * words_f;
-    win_words = need > (float)kWinWordsMax ? kWinWordsMax : (need < 1024.f ? 1024 : (int)need);
+    win_words = need > (float)cap ? cap : (need < 1024.f ? 1024 : (int)need);
   }
   const size_t smem = (size_t)2 * S * 4 + (size_t)win_words * 4;
   VPF_CUDA(launch_pdl(pdl_for_rows((long long)n * (S / kPatch) * (S / kPatch)),
-                      crop_col_kernel<kFromState>, dim3(n), dim3(kColThreads), smem, stream, frame,
+                      crop_col_kernel<kFromState>, dim3(n), dim3(warps * 32), smem, stream, frame,
                       H, W, src, n, ld, w0, h0, (__nv_bfloat16*)out, f16, S, win_words));
   return VPF_OK;
 }
