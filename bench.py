@@ -490,15 +490,16 @@ def main():
 
     shards, calibration = None, None
     if world > 1 and args.shards == "balanced":
-        # 3 timed steps with equal shards; each rank's encoder-side time (events around propagate,
-        # crop and the ViT: no collective inside) sizes its shard for the real run
+        # 8 timed steps (after 3 to reach the power-capped steady state) with equal shards; each
+        # rank's encoder-side time (events around propagate, crop and the ViT: no collective
+        # inside) sizes its shard for the real run
         cal = make_tracker()
         cal.timing = True
         comp = []
-        for i in range(5):
-            cal.step(frames_dev[1 + i])
+        for i in range(11):
+            cal.step(frames_dev[1 + i % (CLIP_FRAMES - 1)])
             torch.cuda.synchronize()
-            if i >= 2:
+            if i >= 3:
                 comp.append(cal.last_timing()[0])
         st = rank_stats(float(np.mean(comp)))
         from vitparticlefiltertracker_b200.exchange import balanced_shards
@@ -617,6 +618,10 @@ def main():
                           f"particles, 2 timed frames of the same clip ({sec:.1f} s/frame)"}
         emit(line)
     if world > 1:
+        barrier()
+        if args.graph:
+            # a captured graph holds NCCL kernels of this communicator; skip the teardown under it
+            os._exit(0)
         dist.destroy_process_group()
 
 

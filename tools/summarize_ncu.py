@@ -70,7 +70,68 @@ def gemm(path):
                         "dram_throughput_pct", "registers")})
 
 
+KEYS = {
+    "duration_ms": "gpu__time_duration.sum",
+    "dram_read_bytes": "dram__bytes_read.sum",
+    "dram_write_bytes": "dram__bytes_write.sum",
+    "dram_throughput_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm_clock_ghz": "sm__cycles_elapsed.avg.per_second",
+    "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "tensor_pipe_active_pct": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "xu_pipe_pct": "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "alu_pipe_pct": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "fma_pipe_pct": "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "lsu_pipe_pct": "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "warp_instructions": "smsp__inst_executed.sum",
+    "registers": "launch__registers_per_thread",
+    "grid": "launch__grid_size", "block": "launch__block_size",
+    "ctas_per_sm_limit_smem": "launch__occupancy_limit_shared_mem",
+    "l2_hit_pct": "lts__t_sector_hit_rate.pct",
+}
+
+
+def kernels(path, out, note=""):
+    """Generic per-launch summary of an `ncu --set full` report -> profiles/<out>.json, with the
+    top stall reasons, stamped with the git commit it was summarised at."""
+    raw = subprocess.run(f"ncu -i {path} --page raw --csv", shell=True, capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+
+    def val(r, name):
+        if name not in col or r[col[name]] in ("", "n/a"):
+            return None
+        v = float(r[col[name]].replace(",", ""))
+        u = units[col[name]]
+        if u in UNIT:
+            v *= UNIT[u]
+        if name == "gpu__time_duration.sum":
+            v *= TIME.get(u, 1.0)
+        if u.lower() == "ghz" or name.endswith("per_second") and u == "Ghz":
+            pass
+        return v
+    stall_cols = [h for h in hdr if "issue_stalled" in h and h.endswith("per_issue_active.ratio")]
+    res = []
+    for r in rows[2:]:
+        d = {"kernel": r[col["Kernel Name"]][:90]}
+        d.update({k: val(r, n) for k, n in KEYS.items()})
+        st = sorted(((float(r[col[h]].replace(",", "")), h) for h in stall_cols
+                     if r[col[h]] not in ("", "n/a")), reverse=True)[:5]
+        d["top_stalls_per_issue"] = {h.split("issue_stalled_")[1].replace("_per_issue_active.ratio", ""): round(v, 2)
+                                     for v, h in st}
+        res.append(d)
+    sha = subprocess.run("git rev-parse --short HEAD", shell=True, capture_output=True, text=True).stdout.strip()
+    json.dump({"source": f"ncu --set full --clock-control none --import-source on; {path}", "note": note,
+               "summarised_at_git": sha, "launches": res}, open(f"profiles/{out}.json", "w"), indent=1)
+    for d in res:
+        print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in d.items()})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 3 and sys.argv[1] == "--kernels":  # --kernels report.ncu-rep out_name [note]
+        kernels(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
+        sys.exit(0)
     if len(sys.argv) > 3 and sys.argv[2] == "--tag":     # launch list of another workload
         launches(sys.argv[1], sys.argv[3], sys.argv[4] + "\n\n" if len(sys.argv) > 4 else None)
         sys.exit(0)

@@ -129,6 +129,28 @@ __device__ __forceinline__ float2 fadd2v(float2 a, float2 b) {
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b, bool f16) { return pack16x2(a, b, f16); }
 
+// 2^x for two values x <= 0 on the FMA pipe (no MUFU): round-to-nearest split x = n + f with the
+// 1.5 * 2^23 magic constant, degree-4 minimax polynomial for 2^f on [-0.5, 0.5] (relative error
+// 2.7e-6 in fp32 Horner form: 200x below the bf16 / 16x below the fp16 rounding of P), then n added
+// to the exponent field.  The softmax is bound by the 16 exp2 lanes per clock of the MUFU unit
+// (profiles/ncu_crop_attn_r02.json: XU pipe the busiest at 47 %, FMA / issue slots at 37 %), so half
+// of the exponentials of every chunk are computed here instead.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);                       // 2^-125: still a normal number after the shift
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 r = fadd2v(x, magic);               // low mantissa bits = round(x)
+  const float2 n = fadd2v(r, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = fadd2v(x, make_float2(-n.x, -n.y));
+  float2 p = ffma2v(make_float2(9.570101276e-03f, 9.570101276e-03f), f,
+                    make_float2(5.591785908e-02f, 5.591785908e-02f));
+  p = ffma2v(p, f, make_float2(2.402474433e-01f, 2.402474433e-01f));
+  p = ffma2v(p, f, make_float2(6.931217909e-01f, 6.931217909e-01f));
+  p = ffma2v(p, f, make_float2(9.999992847e-01f, 9.999992847e-01f));
+  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(r.x) << 23)),
+                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23)));
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                     __nv_bfloat16* __restrict__ out, int n_pairs, int heads, int D, int f16_) {
@@ -285,7 +307,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int j = 0; j < 16; ++j) {
             const float2 a = ffma2v(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])),
                                     c2, nmc2);
-            const float2 p = make_float2(ex2(a.x), ex2(a.y));
+            // alternate pairs between the MUFU unit and the FMA-pipe polynomial
+            const float2 p = (j & 1) ? ex2_poly2(a) : make_float2(ex2(a.x), ex2(a.y));
             l2 = fadd2v(l2, p);
             pk[j] = pack2(p.x, p.y, f16);
           }
