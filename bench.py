@@ -302,6 +302,24 @@ def stage_times(dev, trk, frame, iters=5):
             "K4_resample_ms": t(lambda: ops.resample(cdf.view(1, -1), total, n, 0, 0.37, st, nxt, idx))}
 
 
+def encoder_breakdown(trk, frames_src, steps=3):
+    """In-step device time of the encoder's kernels, summed per kind (vpf_vit_set_timing: an event
+    pair around every launch of the real step, so shares and absolutes are those of the throttled
+    step, unlike the cold serialised ncu launch list).  Every rank steps (collectives); the caller
+    reports rank 0's."""
+    trk.encoder.set_timing(True)
+    acc = {}
+    for i in range(steps + 1):
+        trk.step(frames_src[1 + i % (CLIP_FRAMES - 1)])
+        t = trk.encoder.timing()
+        if i:                                   # the first step settles clocks / caches
+            for k, v in t.items():
+                acc[k] = acc.get(k, 0.0) + v / steps
+    trk.encoder.set_timing(False)
+    acc["sum"] = sum(acc.values())
+    return acc
+
+
 def hbm_kernels(dev, trk, frame, peaks, iters=10):
     """K1 (crop) and K3/K4 (particle update + resampling) timed alone with CUDA events: achieved
     HBM GB/s on their algorithmic bytes against the measured copy peak."""
@@ -558,6 +576,7 @@ def main():
             f"exchange: collectives + PF kernels {x['min']:.2f} ms per step exceed the rank "
             f"spread {c['max'] - c['min']:.2f} ms")
 
+    breakdown = encoder_breakdown(trk, frames_dev) if not args.graph else None
     x16 = args.residual == "fp16"
     roof, gemm_ms = gemm_roofline(dev, trk.n * 197, trk.dim, peaks, x16=x16) if rank == 0 else (None, 0.0)
     hbm = hbm_kernels(dev, trk, frames_dev[1], peaks) if rank == 0 else None
@@ -602,7 +621,8 @@ def main():
                     "h2d_bytes_per_step": int(frames_host[0].numel()),
                     "d2h_bytes_per_step": 40},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roof, "hbm_kernels": hbm, "stages_ms": stages, "tracking": tracking,
+            "roofline": roof, "hbm_kernels": hbm, "stages_ms": stages,
+            "encoder_breakdown_ms": breakdown, "tracking": tracking,
             "clocks": clocks,
         }
         line.update(extras)

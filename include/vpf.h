@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VPF_ABI_VERSION 5
+#define VPF_ABI_VERSION 6
 
 /* 16-bit operand type of crops / ViT activations / weights (fp32 accumulation either way) */
 #define VPF_DTYPE_BF16 0
@@ -132,6 +132,14 @@ int vpf_attention(const void* qkv_bf16, void* out_bf16, int n_crops, int heads, 
                   void* stream);
 /* number of kernels one vpf_vit_forward enqueues (for bench.py's gpu_launches claim).         */
 int vpf_vit_launches(const vpf_vit* h);
+/* Measurement aid (SURVEY.md section 8d "per-stage times"): with timing enabled every launch of a
+ * forward is bracketed by CUDA events on the caller's stream (not capturable in a graph while on);
+ * vpf_vit_timing waits for the last forward and returns its device milliseconds summed per kind:
+ * [0] patch embed  [1] LayerNorm  [2] qkv GEMM  [3] attention  [4] proj GEMM  [5] fc1 GEMM
+ * [6] fc2 GEMM  [7] last block (CLS-only) + final norm.  n_kinds >= VPF_VIT_TIMING_KINDS.        */
+#define VPF_VIT_TIMING_KINDS 8
+int vpf_vit_set_timing(vpf_vit* h, int enable);
+int vpf_vit_timing(vpf_vit* h, float* ms_by_kind, int n_kinds);
 
 /* ---- a6: likelihood, normalisation, ESS, estimate (README.md:8; oracle/pf.py weigh, D9/D10) -
  * vpf_loglik:   logw[i] = cos(emb[i], tmpl) / tau;  local_max[0] = max_i logw[i].

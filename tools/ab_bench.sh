@@ -13,7 +13,8 @@ import json
 d = json.loads(open("gpurun_out/ab_${which}_$i.json").read())
 r = d["roofline"]["detail"]
 print("$which $i: %.2f ms/step  gemm frac %.3f  crop %.3f ms" % (d["ms_per_step"], d["roofline"]["frac"], d["hbm_kernels"]["crop_resize_patchify"]["ms"]),
-      {k: round(v["ms"], 3) for k, v in r.items()})
+      {k: round(v["ms"], 3) for k, v in r.items()},
+      "in-step:", {k: round(v, 2) for k, v in (d.get("encoder_breakdown_ms") or {}).items()})
 PY
   done
 done

@@ -41,6 +41,23 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(out_path: str, defines) -> str:
+    """Builds a second library with extra -D flags (same sources, same ABI) for same-box A/B runs
+    (tools/ab_bench.sh, VPF_LIB_PATH); objects go to a scratch directory."""
+    import tempfile
+    nvcc = _nvcc()
+    with tempfile.TemporaryDirectory() as tmp:
+        objs = []
+        for src in SOURCES:
+            obj = os.path.join(tmp, src.replace(".cu", ".o"))
+            subprocess.run([nvcc, *NVCC_FLAGS, *EXTRA_FLAGS.get(src, []), *[f"-D{d}" for d in defines],
+                            "-c", os.path.join(CSRC, src), "-o", obj], check=True)
+            objs.append(obj)
+        subprocess.run([nvcc, "-shared", "-cudart", "static", "-gencode",
+                        "arch=compute_100a,code=sm_100a", "-o", out_path, *objs], check=True)
+    return out_path
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compiles csrc/*.cu and links libvpf.so.  Safe under torchrun: ranks serialise on a file
     lock (the first one builds, the others find the library up to date), and the library is

@@ -23,6 +23,11 @@
 #include "common.cuh"
 #include "sm100.cuh"
 
+// 1: half of the softmax exponentials on the FMA pipe (ex2_poly2); 0: all on the MUFU unit
+#ifndef VPF_ATTN_POLY_EXP2
+#define VPF_ATTN_POLY_EXP2 1
+#endif
+
 namespace vpf {
 namespace attn {
 
@@ -308,7 +313,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const float2 a = ffma2v(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])),
                                     c2, nmc2);
             // alternate pairs between the MUFU unit and the FMA-pipe polynomial
-            const float2 p = (j & 1) ? ex2_poly2(a) : make_float2(ex2(a.x), ex2(a.y));
+            const float2 p = (VPF_ATTN_POLY_EXP2 && (j & 1)) ? ex2_poly2(a) : make_float2(ex2(a.x), ex2(a.y));
             l2 = fadd2v(l2, p);
             pk[j] = pack2(p.x, p.y, f16);
           }

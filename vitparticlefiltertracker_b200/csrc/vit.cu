@@ -512,7 +512,36 @@ struct vpf_vit {
   // CLS-only last block: strided CLS rows of Xn, compact [n][D] / [n][4D] operands
   CUtensorMap a_xn_cls, a_ocls, a_xnc, a_hc, m_kv_last, m_q_last;
   bool cls_prune = true;
+  // optional in-step kernel timing (vpf_vit_set_timing): an event pair around every launch of a
+  // forward, summed per kind by vpf_vit_timing
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_kind;      // kind of the i-th recorded interval (events 2i, 2i+1)
+  size_t ev_used = 0;
 };
+
+// kinds of vpf_vit_timing's output vector
+enum { kTPatch = 0, kTLayerNorm, kTQkv, kTAttention, kTProj, kTFc1, kTFc2, kTTail, kTKinds };
+
+struct TimedLaunch {
+  vpf_vit* h; cudaStream_t s; bool on;
+  TimedLaunch(vpf_vit* h_, int kind, cudaStream_t s_) : h(h_), s(s_), on(h_->timing) {
+    if (!on) return;
+    while (h->ev_pool.size() < h->ev_used + 2) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      h->ev_pool.push_back(e);
+    }
+    h->ev_kind.push_back(kind);
+    cudaEventRecord(h->ev_pool[h->ev_used], s);
+  }
+  ~TimedLaunch() {
+    if (!on) return;
+    cudaEventRecord(h->ev_pool[h->ev_used + 1], s);
+    h->ev_used += 2;
+  }
+};
+#define VPF_TIMED(kind) TimedLaunch timed_launch__(h, kind, s)
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -564,6 +593,7 @@ int vpf_vit_create(vpf_vit** out, const vpf_vit_config* cfg) {
 }
 
 int vpf_vit_destroy(vpf_vit* h) {
+  if (h) for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
   return VPF_OK;
 }
@@ -641,26 +671,39 @@ static int run_block(vpf_vit* h, const LayerW& w, int n, cudaStream_t s) {
   const int f16 = h->cfg.dtype == VPF_DTYPE_F16;
   const int ln_blocks = (M + 7) / 8;
   int rc;
-  VPF_CUDA(launch_layernorm<__nv_bfloat16>(ln_blocks, s, h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0, h->x16));
   {
+    VPF_TIMED(kTLayerNorm);
+    VPF_CUDA(launch_layernorm<__nv_bfloat16>(ln_blocks, s, h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0, h->x16));
+  }
+  {
+    VPF_TIMED(kTQkv);
     GemmArgs g{M, 3 * D, D, w.qkv_b, h->big, nullptr};
       g.f16 = f16;
     if ((rc = launch_gemm(h->a_xn, w.m_qkv, g, kBiasBf16, s))) return rc;
   }
-  if ((rc = launch_attention(h->big, h->Xn, n, H, h->tokens, &h->a_q, &h->a_kv, s, f16))) return rc;
   {
+    VPF_TIMED(kTAttention);
+    if ((rc = launch_attention(h->big, h->Xn, n, H, h->tokens, &h->a_q, &h->a_kv, s, f16))) return rc;
+  }
+  {
+    VPF_TIMED(kTProj);
     GemmArgs g{M, D, D, w.proj_b, h->X, nullptr};
       g.f16 = f16;
       g.x16 = h->x16;
     if ((rc = launch_gemm(h->a_xn, w.m_proj, g, kBiasResidualF32, s))) return rc;
   }
-  VPF_CUDA(launch_layernorm<__nv_bfloat16>(ln_blocks, s, h->X, D, w.ln2_g, w.ln2_b, h->Xn, M, D, f16 != 0, h->x16));
   {
+    VPF_TIMED(kTLayerNorm);
+    VPF_CUDA(launch_layernorm<__nv_bfloat16>(ln_blocks, s, h->X, D, w.ln2_g, w.ln2_b, h->Xn, M, D, f16 != 0, h->x16));
+  }
+  {
+    VPF_TIMED(kTFc1);
     GemmArgs g{M, 4 * D, D, w.fc1_b, h->big, nullptr};
       g.f16 = f16;
     if ((rc = launch_gemm(h->a_xn, w.m_fc1, g, kBiasGeluBf16, s))) return rc;
   }
   {
+    VPF_TIMED(kTFc2);
     GemmArgs g{M, D, 4 * D, w.fc2_b, h->X, nullptr};
       g.f16 = f16;
       g.x16 = h->x16;
@@ -692,6 +735,7 @@ static int run_last_block_cls(vpf_vit* h, const LayerW& w, int n, float* emb, cu
   const int f16 = h->cfg.dtype == VPF_DTYPE_F16;
   const ClsBufs c = cls_bufs(h, n);
   int rc;
+  VPF_TIMED(kTTail);
   VPF_CUDA(launch_layernorm<__nv_bfloat16>((M + 7) / 8, s, h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0, h->x16));
   {  // K, V for every token: rows [D, 3D) of the fused qkv weight
     GemmArgs g{M, 2 * D, D, w.qkv_b + D, h->big, nullptr};
@@ -756,9 +800,11 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
     h->maps_patches = patches;
   }
 
-  VPF_CUDA(launch_pdl(pdl_for_rows((long long)n * T), cls_init_kernel, dim3((n * D + 255) / 256), dim3(256), 0, s, h->X, h->cls,
-                      h->pos, n, D, T, h->x16));
+  if (h->timing) { h->ev_used = 0; h->ev_kind.clear(); }
   {
+    VPF_TIMED(kTPatch);
+    VPF_CUDA(launch_pdl(pdl_for_rows((long long)n * T), cls_init_kernel, dim3((n * D + 255) / 256), dim3(256), 0, s, h->X, h->cls,
+                        h->pos, n, D, T, h->x16));
     GemmArgs g{M0, D, 768, h->patch_b, h->X, h->pos};
     g.f16 = h->cfg.dtype == VPF_DTYPE_F16;
     g.ppc = h->ppc;
@@ -769,7 +815,29 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
   for (int l = 0; l < full_blocks; ++l)
     if ((rc = run_block(h, h->layers[l], n, s))) return rc;
   if (h->cls_prune) return run_last_block_cls(h, h->layers[L - 1], n, emb, s);
+  VPF_TIMED(kTTail);
   VPF_CUDA(launch_layernorm<float>((n + 7) / 8, s, h->X, (size_t)T * D, h->norm_g, h->norm_b, emb, n, D, false, h->x16));
+  return VPF_OK;
+}
+
+int vpf_vit_set_timing(vpf_vit* h, int enable) {
+  VPF_REQUIRE(h, "vpf_vit_set_timing: null handle");
+  h->timing = enable != 0;
+  h->ev_used = 0;
+  h->ev_kind.clear();
+  return VPF_OK;
+}
+
+int vpf_vit_timing(vpf_vit* h, float* ms_by_kind, int n_kinds) {
+  VPF_REQUIRE(h && ms_by_kind && n_kinds >= kTKinds, "vpf_vit_timing: need room for %d kinds", (int)kTKinds);
+  for (int k = 0; k < n_kinds; ++k) ms_by_kind[k] = 0.f;
+  if (!h->timing || !h->ev_used) return VPF_OK;
+  VPF_CUDA(cudaEventSynchronize(h->ev_pool[h->ev_used - 1]));
+  for (size_t i = 0; i < h->ev_kind.size(); ++i) {
+    float ms = 0.f;
+    VPF_CUDA(cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
+    ms_by_kind[h->ev_kind[i]] += ms;
+  }
   return VPF_OK;
 }
 

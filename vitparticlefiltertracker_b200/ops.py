@@ -321,6 +321,19 @@ class VitEncoder:
                                              _stream()), "vpf_vit_forward")
         return emb
 
+    TIMING_KINDS = ("patch_embed", "layernorm", "qkv", "attention", "proj", "fc1", "fc2",
+                    "last_block_cls_and_norm")
+
+    def set_timing(self, enable: bool):
+        """Bracket every launch of a forward with CUDA events (measurement aid; not capturable)."""
+        _lib.check(self._lib.vpf_vit_set_timing(self._h, 1 if enable else 0), "vpf_vit_set_timing")
+
+    def timing(self) -> dict:
+        """Device milliseconds of the last forward, summed per kernel kind (waits for it)."""
+        buf = (C.c_float * len(self.TIMING_KINDS))()
+        _lib.check(self._lib.vpf_vit_timing(self._h, buf, len(self.TIMING_KINDS)), "vpf_vit_timing")
+        return dict(zip(self.TIMING_KINDS, [float(v) for v in buf]))
+
     def __del__(self):
         try:
             if getattr(self, "_h", None) and self._h.value:
