@@ -75,3 +75,22 @@ def test_flops_formula():
     assert abs(vit_flops_per_crop("vit_tiny_patch16_224") / 1e9 - 2.507) < 0.01
     assert abs(vit_flops_per_crop("vit_base_patch16_224") / 1e9 - 35.126) < 0.01
     assert abs(vit_flops_per_crop("vit_large_patch16_224") / 1e9 - 123.107) < 0.01
+
+
+def test_operand_quantisation_emulation():
+    """oracle.vit.quantise (the FP8 study's emulation): e4m3 keeps 3
+    mantissa bits whatever the per-tensor scale; bf16 / fp16 match torch's own conversions."""
+    import torch
+    from oracle.vit import quantise
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(4096, generator=g) * 3.7
+    assert quantise(x, None) is x
+    assert torch.equal(quantise(x, "bf16"), x.to(torch.bfloat16).float())
+    assert torch.equal(quantise(x, "fp16"), x.to(torch.float16).float())
+    q = quantise(x, "e4m3")
+    big = x.abs() > x.abs().max() * 2.0 ** -6           # the normal range of the scaled format
+    rel = ((q - x).abs() / x.abs())[big]
+    assert float(rel.max()) <= 2.0 ** -4 + 1e-6 and float(rel.mean()) > 2.0 ** -7
+    assert float(quantise(x * 1000, "e4m3").abs().max()) == pytest.approx(float((x * 1000).abs().max()), rel=1e-6)
+    with pytest.raises(ValueError):
+        quantise(x, "int4")

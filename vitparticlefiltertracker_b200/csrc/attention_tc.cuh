@@ -401,5 +401,270 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Run-time token count: the same tcgen05 pipeline for 64 < T < 197 (crop sizes 128 .. 208), where
+// round 1 fell back to the warp-level mma.sync kernel.  Keys are padded to the next multiple of 16
+// (`keys`; the TMA unit zero-fills tokens >= T, the softmax masks them), and a (crop, head) pair has
+// one query tile when T <= 128, two otherwise.  A "unit" is one query tile of one pair; units
+// alternate between the two TMEM buffers / softmax warpgroups whatever the tile count, so with one
+// tile per pair the two warpgroups work on consecutive pairs.  The T = 197 kernel above stays the
+// specialised (fully unrolled) version of this one.
+//   TMEM buffer b at column 256 b:  S [0,keys)  P aliases [0,keys/2)  O [128,192)
+__global__ void __launch_bounds__(kThreads, 1)
+attention_tc_var_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                        __nv_bfloat16* __restrict__ out, int n_pairs, int heads, int D, int f16_,
+                        int T, int keys) {
+  const bool f16 = f16_ != 0;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = base;                                   // [kQStages][128][128 B]
+  uint8_t* sK = sQ + kQStages * kQBytes;                // [kKVStages][<= 208][128 B]
+  uint8_t* sV = sK + kKVStages * kKVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKVStages * kKVBytes);
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = bars + 4;
+  uint64_t* kv_full = bars + 8;
+  uint64_t* kv_empty = bars + 10;
+  uint64_t* s_full = bars + 12;
+  uint64_t* p_full = bars + 14;
+  uint64_t* o_full = bars + 16;
+  uint64_t* buf_empty = bars + 18;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_pairs = (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tpp = T > 128 ? 2 : 1;                       // query tiles per pair
+  const int units = my_pairs * tpp;
+  const uint32_t kv_bytes = (uint32_t)keys * 128u;       // K (or V) tile: keys rows x 128 B
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    for (int i = 0; i < kQStages; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 4); }
+    for (int i = 0; i < kKVStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1); mbar_init(&buf_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, kTmemCols); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int u = 0; u < units; ++u) {
+        const int ip = u / tpp, t = u - ip * tpp;
+        const int pair = (int)blockIdx.x + ip * (int)gridDim.x;
+        const int crop = pair / heads, head = pair - crop * heads;
+        if (t == 0) {
+          const int ks = ip & 1;
+          mbar_wait(&kv_empty[ks], ((ip >> 1) & 1) ^ 1, 10);
+          mbar_arrive_expect_tx(&kv_full[ks], 2 * kv_bytes);
+          tma_load_3d(sK + ks * kKVBytes, &tmKV, &kv_full[ks], D + head * kD, 0, crop);
+          tma_load_3d(sV + ks * kKVBytes, &tmKV, &kv_full[ks], 2 * D + head * kD, 0, crop);
+        }
+        const int qs = u & 3;
+        mbar_wait(&q_empty[qs], ((u >> 2) & 1) ^ 1, 11);
+        mbar_arrive_expect_tx(&q_full[qs], kQBytes);
+        tma_load_3d(sQ + qs * kQBytes, &tmQ, &q_full[qs], head * kD, t * 128, crop);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_16(128, keys, f16);
+      const uint32_t idesc_o = make_idesc_bmn(128, kD, f16);
+      auto issue_s = [&](int u) {
+        const int ip = u / tpp, b = u & 1, qs = u & 3, ks = ip & 1, k = u >> 1;
+        mbar_wait(&q_full[qs], (u >> 2) & 1, 12);
+        mbar_wait(&kv_full[ks], (ip >> 1) & 1, 13);      // already complete for a pair's 2nd tile
+        mbar_wait(&buf_empty[b], (k & 1) ^ 1, 14);
+        tcgen05_fence_after();
+        const uint64_t adesc = make_smem_desc_k_sw128(smem_u32(sQ + qs * kQBytes));
+        const uint64_t bdesc = make_smem_desc_k_sw128(smem_u32(sK + ks * kKVBytes));
+        const uint32_t d = tmem_base + (uint32_t)(b * kBufCols);
+#pragma unroll
+        for (int kk = 0; kk < kD / 16; ++kk)
+          umma_bf16(d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc_s, (uint32_t)(kk != 0));
+        umma_commit(&s_full[b]);
+      };
+      auto issue_pv = [&](int u) {
+        const int ip = u / tpp, t = u - ip * tpp, b = u & 1, ks = ip & 1, k = u >> 1;
+        mbar_wait(&p_full[b], k & 1, 15);
+        tcgen05_fence_after();
+        const uint32_t vaddr = smem_u32(sV + ks * kKVBytes);
+        const uint32_t p = tmem_base + (uint32_t)(b * kBufCols);
+        const uint32_t d = p + (uint32_t)kOCol;
+        const int groups = keys >> 4;
+#pragma unroll 1
+        for (int kk = 0; kk < groups; ++kk)              // 16 keys: 8 packed P columns, 2 V row atoms
+          umma_bf16_ts(d, p + (uint32_t)(kk * 8), make_smem_desc_mn_sw128(vaddr + kk * 2048), idesc_o,
+                       (uint32_t)(kk != 0));
+        umma_commit(&o_full[b]);
+        if (t == tpp - 1) umma_commit(&kv_empty[ks]);    // every MMA of this pair has retired
+      };
+      if (units > 0) issue_s(0);
+      if (units > 1) issue_s(1);
+      for (int u = 0; u < units; ++u) {
+        issue_pv(u);
+        if (u + 2 < units) issue_s(u + 2);
+      }
+    }
+  } else {
+    // ===================== softmax / output warpgroups =====================
+    const int b = (warp - 2) >> 2;                 // TMEM buffer == unit parity
+    const int quarter = warp & 3;                  // TMEM lane quarter
+    const int t = tpp == 2 ? b : 0;                // query tile this warpgroup works on
+    const bool warp_has_rows = (t * 128 + quarter * 32) < T;
+    const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    const uint32_t tbuf = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * kBufCols);
+    const int nchunks = (keys + 31) >> 5;          // 32-column chunks; the last one may be half real
+    for (int u = b; u < units; u += 2) {
+      const int ip = u / tpp, k = u >> 1, qs = u & 3;
+      const int pair = (int)blockIdx.x + ip * (int)gridDim.x;
+      const int crop = pair / heads, head = pair - crop * heads;
+      mbar_wait(&s_full[b], k & 1, 16);
+      tcgen05_fence_after();
+      float inv_l = 0.f;
+      if (warp_has_rows) {
+        uint32_t va[32], vb[32];
+        // ---- pass 1: row maximum over the T real keys ----
+        float m0 = -INFINITY, m1 = -INFINITY;
+        auto max_chunk = [&](const uint32_t (&v)[32], int ch) {
+          if (ch + 1 < nchunks) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              m0 = max3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+              m1 = max3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            }
+          } else {                                 // last chunk: columns >= T are padding
+            const int lim = T - ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < lim) m0 = fmaxf(m0, __uint_as_float(v[j]));
+          }
+        };
+        int ch = 0;
+        tmem_ld_32x32(tbuf, va);
+        tmem_ld_wait();
+        while (true) {
+          if (ch + 1 < nchunks) tmem_ld_32x32(tbuf + (uint32_t)((ch + 1) * 32), vb);
+          max_chunk(va, ch);
+          if (ch + 1 >= nchunks) break;
+          tmem_ld_wait();
+          if (ch + 2 < nchunks) tmem_ld_32x32(tbuf + (uint32_t)((ch + 2) * 32), va);
+          max_chunk(vb, ch + 1);
+          if (ch + 2 >= nchunks) break;
+          tmem_ld_wait();
+          ch += 2;
+        }
+        const float m = fmaxf(m0, m1);
+        const float2 c2 = make_float2(c, c);
+        const float nmc = -m * c;
+        const float2 nmc2 = make_float2(nmc, nmc);
+        // ---- pass 2: p = 2^(s c - m c), row sum, P (bf16 pairs) written in place over S ----
+        float2 l2 = make_float2(0.f, 0.f);
+        auto exp_chunk = [&](const uint32_t (&v)[32], int chn) {
+          uint32_t pk[16];
+          if (chn + 1 < nchunks) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 a = ffma2v(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])),
+                                      c2, nmc2);
+              const float2 p = (VPF_ATTN_POLY_EXP2 && (j & 1)) ? ex2_poly2(a) : make_float2(ex2(a.x), ex2(a.y));
+              l2 = fadd2v(l2, p);
+              pk[j] = pack2(p.x, p.y, f16);
+            }
+          } else {
+            const int lim = T - chn * 32;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float p0 = (2 * j < lim) ? ex2(fmaf(__uint_as_float(v[2 * j]), c, nmc)) : 0.f;
+              const float p1 = (2 * j + 1 < lim) ? ex2(fmaf(__uint_as_float(v[2 * j + 1]), c, nmc)) : 0.f;
+              l2.x += p0; l2.y += p1;
+              pk[j] = pack2(p0, p1, f16);
+            }
+          }
+          tmem_st_32x16(tbuf + (uint32_t)(chn * 16), pk);
+        };
+        ch = 0;
+        tmem_ld_32x32(tbuf, va);
+        tmem_ld_wait();
+        while (true) {
+          if (ch + 1 < nchunks) tmem_ld_32x32(tbuf + (uint32_t)((ch + 1) * 32), vb);
+          exp_chunk(va, ch);
+          if (ch + 1 >= nchunks) break;
+          tmem_ld_wait();
+          if (ch + 2 < nchunks) tmem_ld_32x32(tbuf + (uint32_t)((ch + 2) * 32), va);
+          exp_chunk(vb, ch + 1);
+          if (ch + 2 >= nchunks) break;
+          tmem_ld_wait();
+          ch += 2;
+        }
+        tmem_st_wait();
+        inv_l = 1.0f / (l2.x + l2.y);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);
+      // ---- O = P V is ready: normalise, stage through this unit's Q tile, store coalesced ----
+      mbar_wait(&o_full[b], k & 1, 17);
+      tcgen05_fence_after();
+      uint8_t* stage = sQ + qs * kQBytes + quarter * 32 * 128;     // this warp's 32 rows
+      if (warp_has_rows) {
+        uint32_t v[32];
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          tmem_ld_32x32(tbuf + (uint32_t)(kOCol + hlf * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack2(__uint_as_float(v[q * 8 + 0]) * inv_l, __uint_as_float(v[q * 8 + 1]) * inv_l, f16);
+            o.y = pack2(__uint_as_float(v[q * 8 + 2]) * inv_l, __uint_as_float(v[q * 8 + 3]) * inv_l, f16);
+            o.z = pack2(__uint_as_float(v[q * 8 + 4]) * inv_l, __uint_as_float(v[q * 8 + 5]) * inv_l, f16);
+            o.w = pack2(__uint_as_float(v[q * 8 + 6]) * inv_l, __uint_as_float(v[q * 8 + 7]) * inv_l, f16);
+            const int chunk = hlf * 4 + q;
+            *reinterpret_cast<uint4*>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&buf_empty[b]);     // TMEM buffer may take the next unit's S
+      if (warp_has_rows) {
+        __nv_bfloat16* orow = out + ((size_t)crop * T + (size_t)(t * 128 + quarter * 32)) * D + head * kD;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3), chunk = lane & 7;
+          if (t * 128 + quarter * 32 + r < T) {
+            const uint4 val = *reinterpret_cast<const uint4*>(stage + r * 128 + ((chunk ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(orow + (size_t)r * D + chunk * 8) = val;
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_empty[qs]);       // Q stage may be refilled
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 }  // namespace attn
 }  // namespace vpf

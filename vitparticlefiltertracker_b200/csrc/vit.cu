@@ -345,23 +345,37 @@ static int launch_attention_small(const __nv_bfloat16* qkv, __nv_bfloat16* out, 
   return VPF_OK;
 }
 
-// T = 197 (224-pixel crops): tcgen05 kernel.  Smaller crop sizes: one warp per (crop, head) for
-// T <= 64, the CTA-per-pair mma.sync kernel above that.
+// T = 197 (224-pixel crops): the specialised tcgen05 kernel; 64 < T < 197 (crop sizes 128 .. 208):
+// the same pipeline with a run-time token count; T <= 64: one warp per (crop, head).  The
+// CTA-per-pair mma.sync kernel remains only behind VPF_ATTN=mma (A/B runs).
+static int keys_padded(int tokens) { return (tokens + 15) & ~15; }
+
 static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_crops, int heads,
                             int tokens, const CUtensorMap* mq, const CUtensorMap* mkv,
                             cudaStream_t s, int f16 = 0) {
   const int D = heads * kHeadDim;
   if (tokens <= 32) return launch_attention_small<32>(qkv, out, n_crops, heads, tokens, s, f16);
   if (tokens <= 64) return launch_attention_small<64>(qkv, out, n_crops, heads, tokens, s, f16);
-  if (tokens == attn::kT && attn_use_tc()) {
-    static bool attr[32] = {};
-    if (first_time_on_device(attr))
-      VPF_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, attn::kSmemBytes));
+  if (attn_use_tc()) {
     const int n_pairs = n_crops * heads;
     const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
-    VPF_CUDA(launch_pdl(pdl_for_rows((long long)n_crops * tokens), attn::attention_tc_kernel, dim3(grid), dim3(attn::kThreads),
-                        (size_t)attn::kSmemBytes, s, *mq, *mkv, out, n_pairs, heads, D, f16));
+    const bool pdl = pdl_for_rows((long long)n_crops * tokens);
+    if (tokens == attn::kT) {
+      static bool attr[32] = {};
+      if (first_time_on_device(attr))
+        VPF_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, attn::kSmemBytes));
+      VPF_CUDA(launch_pdl(pdl, attn::attention_tc_kernel, dim3(grid), dim3(attn::kThreads),
+                          (size_t)attn::kSmemBytes, s, *mq, *mkv, out, n_pairs, heads, D, f16));
+    } else {
+      static bool attr[32] = {};
+      if (first_time_on_device(attr))
+        VPF_CUDA(cudaFuncSetAttribute(attn::attention_tc_var_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, attn::kSmemBytes));
+      VPF_CUDA(launch_pdl(pdl, attn::attention_tc_var_kernel, dim3(grid), dim3(attn::kThreads),
+                          (size_t)attn::kSmemBytes, s, *mq, *mkv, out, n_pairs, heads, D, f16, tokens,
+                          keys_padded(tokens)));
+    }
   } else {
     static bool attr[32] = {};
     if (first_time_on_device(attr))
@@ -787,9 +801,9 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
     if ((rc = make_map(&h->a_patches, patches, M0, 768, kBlockM))) return rc;
     if ((rc = make_map(&h->a_xn, h->Xn, M, D, kBlockM))) return rc;
     if ((rc = make_map(&h->a_big, h->big, M, 4 * D, kBlockM))) return rc;
-    if (T == attn::kT) {      // tcgen05 attention (smaller crop sizes use the mma.sync kernels)
+    if (T > 64) {             // tcgen05 attention (T <= 64: the warp-per-pair kernels need no map)
       if ((rc = make_qkv_map(&h->a_q, h->big, n, D, 128, T))) return rc;
-      if ((rc = make_qkv_map(&h->a_kv, h->big, n, D, attn::kKeys, T))) return rc;
+      if ((rc = make_qkv_map(&h->a_kv, h->big, n, D, keys_padded(T), T))) return rc;
     }
     const ClsBufs c = cls_bufs(h, n);
     if ((rc = make_map(&h->a_xn_cls, h->Xn, n, D, kBlockM, (uint64_t)T * D))) return rc;
@@ -874,9 +888,9 @@ int vpf_attention(const void* qkv, void* out, int n_crops, int heads, int tokens
               "vpf_attention: bad arguments (2 <= tokens <= 197)");
   CUtensorMap mq, mkv;
   int rc;
-  if (tokens == attn::kT) {
+  if (tokens > 64) {
     if ((rc = make_qkv_map(&mq, qkv, n_crops, heads * kHeadDim, 128, tokens))) return rc;
-    if ((rc = make_qkv_map(&mkv, qkv, n_crops, heads * kHeadDim, attn::kKeys, tokens))) return rc;
+    if ((rc = make_qkv_map(&mkv, qkv, n_crops, heads * kHeadDim, keys_padded(tokens), tokens))) return rc;
   }
   return launch_attention((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n_crops, heads, tokens,
                           &mq, &mkv, (cudaStream_t)stream);
