@@ -175,3 +175,28 @@ def test_vit_forward_with_nontrivial_biases_and_layernorm_params():
     cos = torch.nn.functional.cosine_similarity(got, want, dim=1)
     print(f"randomised checkpoint: rel-L2 {rel:.3e}, min cos {cos.min():.6f}")
     assert rel < 1.5e-2 and cos.min() > 1 - 1e-3
+
+
+def test_in_step_kernel_timing_hook():
+    """vpf_vit_set_timing / vpf_vit_timing (bench.py's encoder_breakdown_ms): an event pair around
+    every launch of a forward; the per-kind sums cover the forward and change nothing in its result."""
+    from vitparticlefiltertracker_b200 import ops, init_state_dict, pack_for_device, VIT_CONFIGS
+    dev = cuda()
+    model, n = "vit_tiny_patch16_224", 64
+    cfg = VIT_CONFIGS[model]
+    enc = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], n, pack_for_device(model, init_state_dict(model)), dev)
+    patches = (torch.randn(n * 196, 768, device=dev) * 0.5).to(torch.bfloat16)
+    ref = enc.forward(patches, n).clone()
+    assert all(v == 0.0 for v in enc.timing().values())             # off: nothing recorded
+    enc.set_timing(True)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    got = enc.forward(patches, n)
+    e.record()
+    t = enc.timing()
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref)
+    assert set(t) == set(ops.VitEncoder.TIMING_KINDS) and all(v > 0 for v in t.values())
+    assert 0.5 * s.elapsed_time(e) <= sum(t.values()) <= 1.05 * s.elapsed_time(e)
+    enc.set_timing(False)
+    assert torch.equal(enc.forward(patches, n), ref)

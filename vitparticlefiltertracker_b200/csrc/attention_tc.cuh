@@ -23,9 +23,14 @@
 #include "common.cuh"
 #include "sm100.cuh"
 
-// 1: half of the softmax exponentials on the FMA pipe (ex2_poly2); 0: all on the MUFU unit
+// 1: half of the softmax exponentials on the FMA pipe (ex2_poly2); 0 (default): all on the MUFU
+// unit.  Measured (round 2, same-box A/B with in-step kernel timing, profiles/ab_attn_poly_r02.txt):
+// the polynomial makes the kernel 14 % FASTER alone (boost clocks: MUFU-bound) but 21-27 % SLOWER
+// inside the tracking step (16.5 -> 20-21 ms per frame): the encoder's GEMMs hold the SM clock near
+// 1.2 GHz there, and at that clock the kernel is bound by instruction issue, which the polynomial
+// adds to.  Kept as a build-time option only.
 #ifndef VPF_ATTN_POLY_EXP2
-#define VPF_ATTN_POLY_EXP2 1
+#define VPF_ATTN_POLY_EXP2 0
 #endif
 
 namespace vpf {

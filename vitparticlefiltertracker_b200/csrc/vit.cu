@@ -101,6 +101,9 @@ static int make_store_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint
   return VPF_OK;
 }
 
+static int num_sms();
+static int num_sms_any() { return num_sms(); }
+
 static int pick_block_n(int N) {
   if (N % 256 == 0) return 256;
   if (N % 192 == 0) return 192;
@@ -300,10 +303,128 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// LayerNorm of the fp16 residual stream (the per-block hot case: 22 launches per ViT-B frame).
+// In-step timing (bench.py encoder_breakdown_ms, round 2) showed the one-row-per-warp kernel above
+// taking 1.07 ms per launch inside the power-capped step against 0.37 ms alone: the encoder's GEMMs
+// hold the SM clock near 1.2 GHz, and at that clock the kernel is bound by instruction issue and by
+// the churn of 100 000 short-lived blocks, not by HBM.  This version is persistent (each warp walks
+// rows with a grid stride), loads 16-byte vectors (8 halves), issues the next row's loads before
+// it reduces the current one, keeps gamma / beta in shared memory, and does its arithmetic as
+// packed fp32x2 (FADD2 / FFMA2): ~130 instead of ~240 instructions per row and lane.  Same
+// arithmetic as above (fp32 mean, centred sum of squares, eps 1e-6), so results are unchanged up to
+// the fp32 rounding of the packed operations.
+template <int NV>                           // 16-byte vectors per lane: D <= NV * 256
+__global__ void __launch_bounds__(256) layernorm16_kernel(const __half* __restrict__ x,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta,
+                                                           uint16_t* __restrict__ out, int rows,
+                                                           int D, bool f16) {
+  extern __shared__ __align__(16) float s_gb[];          // [D] gamma | [D] beta
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) { s_gb[i] = gamma[i]; s_gb[D + i] = beta[i]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int nvec = D >> 3;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const float inv_d = 1.0f / (float)D;
+  pdl_wait();
+  uint4 raw[NV];
+  auto load_row = [&](int r) {
+    const uint4* p = reinterpret_cast<const uint4*>(x + (size_t)r * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + 32 * i < nvec) raw[i] = p[lane + 32 * i];
+  };
+  if (row < rows) load_row(row);
+  for (; row < rows; row += warps) {
+    float2 v[NV][4];
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+        v[i][0] = unpack_h2(raw[i].x); v[i][1] = unpack_h2(raw[i].y);
+        v[i][2] = unpack_h2(raw[i].z); v[i][3] = unpack_h2(raw[i].w);
+        acc = fadd2(acc, fadd2(fadd2(v[i][0], v[i][1]), fadd2(v[i][2], v[i][3])));
+      }
+    }
+    if (row + warps < rows) load_row(row + warps);        // next row in flight during the reductions
+    const float mean = warp_sum(acc.x + acc.y) * inv_d;
+    const float2 nmean = make_float2(-mean, -mean);
+    float2 sq = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[i][k] = fadd2(v[i][k], nmean);
+          sq = ffma2(v[i][k], v[i][k], sq);
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq.x + sq.y) * inv_d + 1e-6f);
+    const float2 rstd2 = make_float2(rstd, rstd);
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)row * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        const float4 g0 = *reinterpret_cast<const float4*>(s_gb + vi * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(s_gb + vi * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(s_gb + D + vi * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(s_gb + D + vi * 8 + 4);
+        const float2 y0 = ffma2(ffma2(v[i][0], rstd2, make_float2(0.f, 0.f)), make_float2(g0.x, g0.y), make_float2(b0.x, b0.y));
+        const float2 y1 = ffma2(ffma2(v[i][1], rstd2, make_float2(0.f, 0.f)), make_float2(g0.z, g0.w), make_float2(b0.z, b0.w));
+        const float2 y2 = ffma2(ffma2(v[i][2], rstd2, make_float2(0.f, 0.f)), make_float2(g1.x, g1.y), make_float2(b1.x, b1.y));
+        const float2 y3 = ffma2(ffma2(v[i][3], rstd2, make_float2(0.f, 0.f)), make_float2(g1.z, g1.w), make_float2(b1.z, b1.w));
+        uint4 pk;
+        pk.x = pack16x2(y0.x, y0.y, f16); pk.y = pack16x2(y1.x, y1.y, f16);
+        pk.z = pack16x2(y2.x, y2.y, f16); pk.w = pack16x2(y3.x, y3.y, f16);
+        o[vi] = pk;
+      }
+    }
+  }
+}
+
+template <int NV>
+static cudaError_t launch_layernorm16_nv(cudaStream_t s, const __half* x, const float* gamma,
+                                         const float* beta, uint16_t* out, int rows, int D, bool f16) {
+  // persistent: exactly as many blocks as are resident at once (a later wave would start its
+  // grid-stride share late), never more warps than rows
+  static int per_sm[32] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& occ = per_sm[dev & 31];
+  if (!occ) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm16_kernel<NV>, 256,
+                                                      (size_t)2 * 1024 * sizeof(float)) != cudaSuccess || occ < 1)
+      occ = 2;
+  }
+  int blocks = num_sms_any() * occ;
+  const int need = (rows + 7) / 8;
+  if (blocks > need) blocks = need;
+  return launch_pdl(pdl_for_rows(rows), layernorm16_kernel<NV>, dim3(blocks), dim3(256),
+                    (size_t)2 * D * sizeof(float), s, x, gamma, beta, out, rows, D, f16);
+}
+
 template <typename OutT>
 static cudaError_t launch_layernorm(int blocks, cudaStream_t s, const float* x, size_t row_stride,
                                     const float* gamma, const float* beta, OutT* out, int rows,
                                     int D, bool f16 = false, bool x16 = false) {
+  // the hot case: contiguous fp16 stream, 16-bit output, D a multiple of 8 up to 1024
+  // (-DVPF_LN_LEGACY=1 builds the A/B variant that keeps the one-row-per-warp kernel everywhere)
+#ifndef VPF_LN_LEGACY
+#define VPF_LN_LEGACY 0
+#endif
+  if (!VPF_LN_LEGACY && sizeof(OutT) == 2 && x16 && row_stride == (size_t)D && D % 8 == 0 && D <= 1024) {
+    const __half* xh = reinterpret_cast<const __half*>(x);
+    uint16_t* o = reinterpret_cast<uint16_t*>(out);
+    if (D <= 256) return launch_layernorm16_nv<1>(s, xh, gamma, beta, o, rows, D, f16);
+    if (D <= 512) return launch_layernorm16_nv<2>(s, xh, gamma, beta, o, rows, D, f16);
+    if (D <= 768) return launch_layernorm16_nv<3>(s, xh, gamma, beta, o, rows, D, f16);
+    return launch_layernorm16_nv<4>(s, xh, gamma, beta, o, rows, D, f16);
+  }
   return launch_pdl(pdl_for_rows(rows), layernorm_kernel<OutT>, dim3(blocks), dim3(256), 0, s, x, row_stride, gamma, beta,
                     out, rows, D, f16, x16);
 }
