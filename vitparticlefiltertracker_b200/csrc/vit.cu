@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // arithmetic as above (fp32 mean, centred sum of squares, eps 1e-6), so results are unchanged up to
 // the fp32 rounding of the packed operations.
 template <int NV>                           // 16-byte vectors per lane: D <= NV * 256
-__global__ void __launch_bounds__(256) layernorm16_kernel(const __half* __restrict__ x,
+__global__ void __launch_bounds__(256, (NV <= 3 ? 4 : 3)) layernorm16_kernel(const __half* __restrict__ x,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta,
                                                            uint16_t* __restrict__ out, int rows,
@@ -330,6 +330,8 @@ __global__ void __launch_bounds__(256) layernorm16_kernel(const __half* __restri
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const float inv_d = 1.0f / (float)D;
   pdl_wait();
+  // one row in registers ahead of the one being reduced, and the rows after it pulled into L2
+  // with prefetch instructions (no registers): HBM latency is covered three rows deep per warp
   uint4 raw[NV];
   auto load_row = [&](int r) {
     const uint4* p = reinterpret_cast<const uint4*>(x + (size_t)r * D);
@@ -337,7 +339,13 @@ __global__ void __launch_bounds__(256) layernorm16_kernel(const __half* __restri
     for (int i = 0; i < NV; ++i)
       if (lane + 32 * i < nvec) raw[i] = p[lane + 32 * i];
   };
+  auto prefetch_row = [&](int r) {                       // one 128-byte line per lane
+    if (r < rows && lane * 64 < D)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (size_t)r * D + lane * 64));
+  };
   if (row < rows) load_row(row);
+  prefetch_row(row + warps);
+  prefetch_row(row + 2 * warps);
   for (; row < rows; row += warps) {
     float2 v[NV][4];
     float2 acc = make_float2(0.f, 0.f);
@@ -350,6 +358,7 @@ __global__ void __launch_bounds__(256) layernorm16_kernel(const __half* __restri
       }
     }
     if (row + warps < rows) load_row(row + warps);        // next row in flight during the reductions
+    prefetch_row(row + 3 * warps);
     const float mean = warp_sum(acc.x + acc.y) * inv_d;
     const float2 nmean = make_float2(-mean, -mean);
     float2 sq = make_float2(0.f, 0.f);
@@ -365,6 +374,7 @@ __global__ void __launch_bounds__(256) layernorm16_kernel(const __half* __restri
     }
     const float rstd = rsqrtf(warp_sum(sq.x + sq.y) * inv_d + 1e-6f);
     const float2 rstd2 = make_float2(rstd, rstd);
+    const float2 zero2 = make_float2(0.f, 0.f);
     uint4* o = reinterpret_cast<uint4*>(out + (size_t)row * D);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -374,10 +384,10 @@ __global__ void __launch_bounds__(256) layernorm16_kernel(const __half* __restri
         const float4 g1 = *reinterpret_cast<const float4*>(s_gb + vi * 8 + 4);
         const float4 b0 = *reinterpret_cast<const float4*>(s_gb + D + vi * 8);
         const float4 b1 = *reinterpret_cast<const float4*>(s_gb + D + vi * 8 + 4);
-        const float2 y0 = ffma2(ffma2(v[i][0], rstd2, make_float2(0.f, 0.f)), make_float2(g0.x, g0.y), make_float2(b0.x, b0.y));
-        const float2 y1 = ffma2(ffma2(v[i][1], rstd2, make_float2(0.f, 0.f)), make_float2(g0.z, g0.w), make_float2(b0.z, b0.w));
-        const float2 y2 = ffma2(ffma2(v[i][2], rstd2, make_float2(0.f, 0.f)), make_float2(g1.x, g1.y), make_float2(b1.x, b1.y));
-        const float2 y3 = ffma2(ffma2(v[i][3], rstd2, make_float2(0.f, 0.f)), make_float2(g1.z, g1.w), make_float2(b1.z, b1.w));
+        const float2 y0 = ffma2(ffma2(v[i][0], rstd2, zero2), make_float2(g0.x, g0.y), make_float2(b0.x, b0.y));
+        const float2 y1 = ffma2(ffma2(v[i][1], rstd2, zero2), make_float2(g0.z, g0.w), make_float2(b0.z, b0.w));
+        const float2 y2 = ffma2(ffma2(v[i][2], rstd2, zero2), make_float2(g1.x, g1.y), make_float2(b1.x, b1.y));
+        const float2 y3 = ffma2(ffma2(v[i][3], rstd2, zero2), make_float2(g1.z, g1.w), make_float2(b1.z, b1.w));
         uint4 pk;
         pk.x = pack16x2(y0.x, y0.y, f16); pk.y = pack16x2(y1.x, y1.y, f16);
         pk.z = pack16x2(y2.x, y2.y, f16); pk.w = pack16x2(y3.x, y3.y, f16);
