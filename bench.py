@@ -196,16 +196,17 @@ def source_hash(*names):
     return h.hexdigest()[:16]
 
 
-def ncu_traffic():
+def ncu_traffic(residual):
     """DRAM bytes of the GEMM family from the newest committed `ncu --set full` capture whose
-    source stamp matches the GEMM sources of this build; (None, why) otherwise."""
+    source stamp matches the GEMM sources of this build and whose residual-stream type is the
+    one being run; (None, why) otherwise."""
     cur = source_hash("gemm.cuh", "sm100.cuh")
     for name in ("ncu_gemm_r02.json", "ncu_gemm_r01.json"):
         prof = os.path.join(ROOT, "profiles", name)
         if not os.path.exists(prof):
             continue
         pj = json.load(open(prof))
-        if pj.get("source_sha16") != cur:
+        if pj.get("source_sha16") != cur or pj.get("residual", "fp32") != residual:
             continue
         return (pj["gemm_family_traffic_bytes_per_block"],
                 f"profiles/{name} (capture of git {pj.get('git_sha', '?')}, source stamp {cur}): "
@@ -257,7 +258,7 @@ def gemm_roofline(dev, M, D, peaks, reps=2, x16=False):
     peak = peaks["tflops_sustained"]
     traffic, traffic_src = None, None
     if M == 4096 * 197 and D == 768:                       # captures are of this exact shape
-        traffic, traffic_src = ncu_traffic()
+        traffic, traffic_src = ncu_traffic("fp16" if x16 else "fp32")
     return {"bound": "tensor", "kernel": "gemm_bf16_kernel<tcgen05, cta_group::2> (qkv+proj+fc1+fc2 of one block)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_burst": peaks["tflops_burst"], "frac_of_burst_peak": achieved / peaks["tflops_burst"],
