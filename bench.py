@@ -215,9 +215,11 @@ def ncu_traffic(residual):
     return None, f"no committed ncu capture matches this build's GEMM sources (stamp {cur})"
 
 
-def gemm_roofline(dev, M, D, peaks, reps=2, x16=False):
+def gemm_roofline(dev, M, D, peaks, reps=2, x16=False, fold=False):
     """Times every GEMM launch of a 12-block encoder pass (qkv, proj, fc1, fc2 at the real M)
-    with CUDA events on the launching stream, inside a sustained loop."""
+    with CUDA events on the launching stream, inside a sustained loop.  `fold`: the kernels the
+    default fp16-stream encoder really launches -- qkv / fc1 with the LayerNorm folded in (A = the
+    stream, statistics from partial sums), proj / fc2 leaving those sums in their epilogues."""
     from vitparticlefiltertracker_b200 import ops
     xn = (torch.randn(M, D, device=dev) * 0.5).to(torch.bfloat16)
     big = torch.empty(M, 4 * D, dtype=torch.bfloat16, device=dev)
@@ -226,12 +228,21 @@ def gemm_roofline(dev, M, D, peaks, reps=2, x16=False):
     ws = {n: ((torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16),
               torch.zeros(N, device=dev)) for n, N, K, _ in shapes}
     qkv_out = big.view(-1)[: M * 3 * D].view(M, 3 * D)
+    if fold:
+        X.copy_(torch.randn(M, D, device=dev).to(X.dtype))
+        parts = torch.zeros((ops.ln_stats_parts(D), M, 2), dtype=torch.float32, device=dev)
+        wf = {n: ws[n][0].to(torch.float16) for n in ("qkv", "fc1")}    # folded weights are fp16
 
     def one(name, N, K, mode):
         w, b = ws[name]
         a = big if name == "fc2" else xn
         out = X if mode == 2 else (qkv_out if name == "qkv" else big)
-        ops.gemm_bf16(a, w, b, mode, out=out)
+        if not fold:
+            ops.gemm_bf16(a, w, b, mode, out=out)
+        elif mode == 2:
+            ops.gemm_residual_stats(a, w, b, X, out=parts)
+        else:
+            ops.gemm_ln(X, wf[name], b, parts, gelu=(mode == 1), out=out)
 
     for name, N, K, mode in shapes:          # warm-up
         one(name, N, K, mode)
@@ -259,7 +270,8 @@ def gemm_roofline(dev, M, D, peaks, reps=2, x16=False):
     traffic, traffic_src = None, None
     if M == 4096 * 197 and D == 768:                       # captures are of this exact shape
         traffic, traffic_src = ncu_traffic("fp16" if x16 else "fp32")
-    return {"bound": "tensor", "kernel": "gemm_bf16_kernel<tcgen05, cta_group::2> (qkv+proj+fc1+fc2 of one block)",
+    return {"bound": "tensor", "kernel": "gemm_bf16_kernel<tcgen05, cta_group::2> (qkv+proj+fc1+fc2 of one block"
+                                         + ("; LayerNorm folded into qkv / fc1, row sums from proj / fc2)" if fold else ")"),
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_burst": peaks["tflops_burst"], "frac_of_burst_peak": achieved / peaks["tflops_burst"],
             "peak_source": peaks["source"] + ", sustained bf16", "traffic": traffic,
@@ -579,7 +591,8 @@ def main():
 
     breakdown = encoder_breakdown(trk, frames_dev) if not args.graph else None
     x16 = args.residual == "fp16"
-    roof, gemm_ms = gemm_roofline(dev, trk.n * 197, trk.dim, peaks, x16=x16) if rank == 0 else (None, 0.0)
+    roof, gemm_ms = gemm_roofline(dev, trk.n * 197, trk.dim, peaks, x16=x16,
+                                   fold=trk.encoder.ln_fold == 2) if rank == 0 else (None, 0.0)
     hbm = hbm_kernels(dev, trk, frames_dev[1], peaks) if rank == 0 else None
     stages = stage_times(dev, trk, frames_dev[1]) if rank == 0 and not args.graph else None
     extras = {}
@@ -614,7 +627,10 @@ def main():
             "config": dict(workload_config(n_gpus, args.model, args.particles_per_gpu),
                            operands=args.dtype, residual_stream=args.residual,
                            shards=(trk.shards if n_gpus > 1 else None),
-                           cuda_graph=bool(args.graph)),
+                           cuda_graph=bool(args.graph),
+                           layernorm=("folded into qkv / fc1 (row sums from the proj / fc2 epilogues)",
+                                      "folded into qkv / fc1 (row-statistics kernel)")[trk.encoder.ln_fold % 2]
+                           if trk.encoder.ln_fold else "separate kernels"),
             "frames_per_s": args.steps / (ms_dev / 1e3),
             "step_tflops_per_gpu": trk.n * fl / (ms_step / 1e3) / 1e12,
             "step_frac_of_sustained_peak": trk.n * fl / (ms_step / 1e3) / 1e12 / peaks["tflops_sustained"],

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VPF_ABI_VERSION 6
+#define VPF_ABI_VERSION 7
 
 /* 16-bit operand type of crops / ViT activations / weights (fp32 accumulation either way) */
 #define VPF_DTYPE_BF16 0
@@ -130,6 +130,32 @@ int vpf_layernorm(const float* x, const float* gamma, const float* beta, void* o
 /* qkv: bf16 [n_crops*tokens][3*64*heads], out: bf16 [n_crops*tokens][64*heads]; 2 <= tokens <= 197 */
 int vpf_attention(const void* qkv_bf16, void* out_bf16, int n_crops, int heads, int tokens,
                   void* stream);
+/* LayerNorm folded into the GEMMs that consume it (fp16 residual stream only; README.md:7; the
+ * arithmetic of oracle/vit.py's norm1 -> qkv and norm2 -> fc1, reassociated):
+ *     LN(x) W^T + b  =  r (x W'^T) + b',   W'_jk = gamma_k W_jk - mean_k(gamma_k W_jk),  b' = b + W beta
+ * (r = 1/sqrt(var(x) + eps); subtracting each weight row's mean over k makes x W'^T equal to
+ * (x - mean(x)) (gamma (.) W)^T, so the row mean is never needed).  The fp16 stream itself is the A
+ * operand and the normalised activation never touches HBM.
+ * dev_ptrs: 4 per block, in block order: qkv_wf fp16 [3D][D], qkv_bf f32 [3D], fc1_wf fp16 [4D][D],
+ * fc1_bf f32 [4D].
+ * W' is fp16 whatever cfg.dtype says: both MMA operands must share one 16-bit type and A is the
+ * fp16 stream; the GEMMs' outputs stay in cfg.dtype.
+ * The row statistics (mu, r) come from the residual GEMMs' epilogues as per-column-group partial
+ * sums (env VPF_LN_FOLD=kernel: from a row-statistics kernel; VPF_LN_FOLD=0: folding ignored).
+ * vpf_vit_ln_fold: 0 = not folded, 1 = statistics kernel, 2 = epilogue sums.                     */
+int vpf_vit_set_ln_fold(vpf_vit* h, const void* const* dev_ptrs, int n_ptrs);
+int vpf_vit_ln_fold(const vpf_vit* h);
+/* test hooks of the folded path: column groups a D-wide residual GEMM splits a row into; final
+ * row statistics stats[rows][2] = (mean, 1/sqrt(var + 1e-6)) of an fp16 [rows][D] matrix; the
+ * folded GEMM (X16, Wf fp16; out in `dtype`; stats_parts = 0: stats = [M][2] final; > 0: [stats_parts][M][2] partial (sum x,
+ * sum x^2)); the fp16-stream residual GEMM that also writes those partial sums
+ * (stats_out f32 [vpf_ln_stats_parts(N)][M][2]).                                                  */
+int vpf_ln_stats_parts(int D);
+int vpf_rowstats16(const void* x16, float* stats, int rows, int D, void* stream);
+int vpf_gemm_ln(const void* X16, const void* Wf, const float* bias_f, const float* stats,
+                int stats_parts, void* out, int M, int N, int K, int gelu, int dtype, void* stream);
+int vpf_gemm_residual_stats(const void* A, const void* W, const float* bias, void* x16,
+                            float* stats_out, int M, int N, int K, int dtype, void* stream);
 /* number of kernels one vpf_vit_forward enqueues (for bench.py's gpu_launches claim).         */
 int vpf_vit_launches(const vpf_vit* h);
 /* Measurement aid (SURVEY.md section 8d "per-stage times"): with timing enabled every launch of a

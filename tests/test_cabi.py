@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/vpf.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(names)
-    assert lib.vpf_abi_version() == 6
+    assert lib.vpf_abi_version() == 7
 
 
 def test_host_only_entry_points():

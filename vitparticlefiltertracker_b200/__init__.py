@@ -7,7 +7,7 @@ from .multistream import MultiStreamTracker  # noqa: F401
 from .ingest import FrameIngest, track  # noqa: F401
 from . import sources  # noqa: F401
 from .vit_weights import (VIT_CONFIGS, flops_per_crop, init_state_dict, load_checkpoint,  # noqa: F401
-                          pack_for_device)
+                          pack_for_device, pack_ln_fold)
 
 __all__ = ["Tracker", "MultiStreamTracker", "FrameIngest", "track", "State", "VIT_CONFIGS", "flops_per_crop", "init_state_dict",
-           "load_checkpoint", "pack_for_device"]
+           "load_checkpoint", "pack_for_device", "pack_ln_fold"]

@@ -19,7 +19,7 @@ class VitConfig(C.Structure):
 
 DTYPE_BF16, DTYPE_F16 = 0, 1
 RESIDUAL_F32, RESIDUAL_F16 = 0, 1
-ABI_VERSION = 6          # VPF_ABI_VERSION in include/vpf.h
+ABI_VERSION = 7          # VPF_ABI_VERSION in include/vpf.h
 
 
 # name -> (restype, argtypes); mirrors include/vpf.h one to one
@@ -53,6 +53,14 @@ SIGNATURES = {
     "vpf_layernorm": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                                _c_void_p]),
     "vpf_attention": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "vpf_vit_set_ln_fold": (_c_int, [_c_void_p, C.POINTER(_c_void_p), _c_int]),
+    "vpf_vit_ln_fold": (_c_int, [_c_void_p]),
+    "vpf_ln_stats_parts": (_c_int, [_c_int]),
+    "vpf_rowstats16": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
+    "vpf_gemm_ln": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p,
+                             _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "vpf_gemm_residual_stats": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
+                                         _c_int, _c_int, _c_int, _c_void_p]),
     "vpf_vit_launches": (_c_int, [_c_void_p]),
     "vpf_vit_set_timing": (_c_int, [_c_void_p, _c_int]),
     "vpf_vit_timing": (_c_int, [_c_void_p, _c_void_p, _c_int]),

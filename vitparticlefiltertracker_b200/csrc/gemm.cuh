@@ -28,8 +28,21 @@ enum GemmMode : int {
   kPatchEmbedF32 = 3,  // X f32 [(r/P)*(P+1) + 1 + r%P][N] = acc + bias + pos[1 + r%P][N], P = ppc
   // internal variant of mode 2, chosen by the launcher for small K (HBM-bound GEMMs such as proj):
   // the fp32 residual tile is loaded, updated in place and stored entirely by the TMA unit
-  kBiasResidualF32Tma = 4
+  kBiasResidualF32Tma = 4,
+  // LayerNorm folded into the GEMM that consumes it (fp16 residual stream only).  A = the residual
+  // stream X itself (fp16); W' = (gamma (.) W) with each row's mean over k subtracted (stored in
+  // fp16), so that x W'^T = (x - mu) (gamma (.) W)^T without knowing mu; b' = b + W beta:
+  //   LN(x) W^T + b  =  r (x W'^T) + b'              (r = the row's 1/sqrt(var + eps))
+  // The normalised activation is never written to or read from HBM, and the epilogue costs what the
+  // plain bias epilogue costs (one FMA instead of one add).  r comes either final from
+  // rowstats16_kernel or from per-column-group partial sums (sum x, sum x^2) that the producing
+  // residual GEMM's epilogue leaves behind (GemmArgs::stats_out).
+  kLnBiasBf16 = 5,      // out 16-bit [M][N] = r acc + b'
+  kLnBiasGeluBf16 = 6   // out 16-bit [M][N] = gelu(r acc + b')
 };
+__host__ __device__ constexpr bool mode_out16(int m) { return m <= 1 || m == 5 || m == 6; }
+__host__ __device__ constexpr bool mode_ln(int m) { return m == 5 || m == 6; }
+__host__ __device__ constexpr bool mode_gelu(int m) { return m == 1 || m == 6; }
 
 struct GemmArgs {
   int M, N, K;
@@ -39,6 +52,17 @@ struct GemmArgs {
   int f16 = 0;   // 16-bit operand / output type: 0 = bf16, 1 = fp16
   int ppc = 196; // patch-embed mode: patches per crop (196 at crop size 224); tokens = ppc + 1
   int x16 = 0;   // residual modes: the residual stream X is fp16 (saturating) instead of fp32
+  // LayerNorm-folded modes (5, 6): the row statistics of A.
+  //   stats_parts == 0: stats[r * stats_stride] = (mu, r) final;
+  //   stats_parts  > 0: stats[p * stats_ld + r * stats_stride] = (sum x, sum x^2) of column group p
+  const float2* stats = nullptr;
+  int stats_parts = 0;
+  int stats_stride = 1;
+  size_t stats_ld = 0;
+  // residual modes (2, 4) with an fp16 stream: if set, the epilogue leaves the partial row sums of
+  // the UPDATED (rounded) stream in stats_out[(n_blk * 2 + column half) * stats_out_ld + row]
+  float2* stats_out = nullptr;
+  size_t stats_out_ld = 0;
 };
 
 static constexpr int kBlockM = 128;
@@ -51,7 +75,7 @@ static constexpr int kMaxEpiWarps = 16;
 // read-modify-write epilogues are memory-bound and need registers for loads in flight.
 template <int BLOCK_N, int MODE>
 struct EpiCfg {
-  static constexpr int kGroups = (MODE <= 1) ? (BLOCK_N == 192 ? 3 : 4) : 2;
+  static constexpr int kGroups = mode_out16(MODE) ? (BLOCK_N == 192 ? 3 : 4) : 2;
   static constexpr int kWarps = 4 * kGroups;
   static constexpr int kThreads = 64 + 32 * kWarps;
   static constexpr int kColsPerWarp = BLOCK_N / kGroups;
@@ -71,7 +95,7 @@ struct GemmCfg {
   // bf16 modes: one 2 KB slab per warp; residual mode: two 4 KB TMA buffers per warp (the fp32
   // residual tile is loaded, updated in place and stored by the TMA unit); patch embed: 4 KB slab
   static constexpr int kEpiBytes =
-      EpiCfg<BLOCK_N, MODE>::kWarps * ((MODE <= 1) ? 2048 : (MODE == 4 ? 8192 : 4096));
+      EpiCfg<BLOCK_N, MODE>::kWarps * (mode_out16(MODE) ? 2048 : (MODE == 4 ? 8192 : 4096));
   static constexpr int kStagesMax = (227 * 1024 - kEpiBytes - 1024 - 512) / kStageBytes;
   static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
   static constexpr int kTmemCols = (2 * BLOCK_N > 256) ? 512 : 256;
@@ -130,12 +154,38 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 //   phase 2 (transposed: consecutive lanes = consecutive 16-byte pieces of one row): read the
 //           slab back and touch global memory fully coalesced (a warp instruction covers whole
 //           64/128-byte row segments instead of 32 different cache lines).
+// Row statistics of the LayerNorm-folded modes -> r = 1/sqrt(var + eps) of the row.
+__device__ __forceinline__ float load_ln_rstd(const GemmArgs& g, int row) {
+  const size_t idx = (size_t)row * (size_t)g.stats_stride;
+  if (g.stats_parts == 0) {
+    return __ldg(g.stats + idx).y;
+  } else {
+    float s = 0.f, q = 0.f;                            // summed in a fixed order: batch-invariant
+    if (g.stats_parts <= 8) {                          // all loads in flight at once
+      float2 v[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p)
+        v[p] = p < g.stats_parts ? __ldg(g.stats + (size_t)p * g.stats_ld + idx) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < 8; ++p) { s += v[p].x; q += v[p].y; }
+    } else {
+      for (int p = 0; p < g.stats_parts; ++p) {
+        const float2 v = __ldg(g.stats + (size_t)p * g.stats_ld + idx);
+        s += v.x; q += v.y;
+      }
+    }
+    const float inv_d = 1.0f / (float)g.K;
+    const float mu = s * inv_d;
+    return rsqrtf(fmaxf(fmaf(-mu, mu, q * inv_d), 0.f) + 1e-6f);
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const GemmArgs& g,
                                                const CUtensorMap* tmC, uint8_t* slab, int row0,
-                                               int col, int lane) {
+                                               int col, int lane, float rstd, float2 (&st)[8]) {
   const float4* b4 = reinterpret_cast<const float4*>(g.bias + col);
-  if (MODE == kBiasBf16 || MODE == kBiasGeluBf16) {
+  if (mode_out16(MODE)) {
     // slab rows are 64 B (32 bf16): piece j of row r lives at r*64 + ((j ^ ((r>>1)&3)) << 4)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -143,12 +193,20 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const float4 b = __ldg(b4 + q * 2 + h);
-        f[h * 2 + 0] = fadd2(make_float2(__uint_as_float(v[q * 8 + h * 4 + 0]),
-                                         __uint_as_float(v[q * 8 + h * 4 + 1])), make_float2(b.x, b.y));
-        f[h * 2 + 1] = fadd2(make_float2(__uint_as_float(v[q * 8 + h * 4 + 2]),
-                                         __uint_as_float(v[q * 8 + h * 4 + 3])), make_float2(b.z, b.w));
+        const float2 a01 = make_float2(__uint_as_float(v[q * 8 + h * 4 + 0]),
+                                       __uint_as_float(v[q * 8 + h * 4 + 1]));
+        const float2 a23 = make_float2(__uint_as_float(v[q * 8 + h * 4 + 2]),
+                                       __uint_as_float(v[q * 8 + h * 4 + 3]));
+        if (mode_ln(MODE)) {
+          const float2 r2 = make_float2(rstd, rstd);
+          f[h * 2 + 0] = ffma2(r2, a01, make_float2(b.x, b.y));
+          f[h * 2 + 1] = ffma2(r2, a23, make_float2(b.z, b.w));
+        } else {
+          f[h * 2 + 0] = fadd2(a01, make_float2(b.x, b.y));
+          f[h * 2 + 1] = fadd2(a23, make_float2(b.z, b.w));
+        }
       }
-      if (MODE == kBiasGeluBf16) {
+      if (mode_gelu(MODE)) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) f[e] = gelu_erf2(f[e]);
       }
@@ -222,8 +280,17 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
       if (dst[i]) {
         float4 o;
         o.x = a.x + res[i].x; o.y = a.y + res[i].y; o.z = a.z + res[i].z; o.w = a.w + res[i].w;
-        if (x16) *reinterpret_cast<uint2*>(dst[i]) = make_uint2(pack_h2_sat(o.x, o.y), pack_h2_sat(o.z, o.w));
-        else *reinterpret_cast<float4*>(dst[i]) = o;
+        if (x16) {
+          const uint2 pk = make_uint2(pack_h2_sat(o.x, o.y), pack_h2_sat(o.z, o.w));
+          *reinterpret_cast<uint2*>(dst[i]) = pk;
+          if (MODE == kBiasResidualF32 && g.stats_out) {   // sums of the stream as stored
+            const float2 y0 = unpack_h2(pk.x), y1 = unpack_h2(pk.y);
+            st[i].x += (y0.x + y0.y) + (y1.x + y1.y);
+            st[i].y = fmaf(y0.x, y0.x, fmaf(y0.y, y0.y, fmaf(y1.x, y1.x, fmaf(y1.y, y1.y, st[i].y))));
+          }
+        } else {
+          *reinterpret_cast<float4*>(dst[i]) = o;
+        }
       }
     }
   }
@@ -311,7 +378,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && leader) {
-      const uint32_t idesc = make_idesc_16(kBlockM * CTAS, BLOCK_N, g.f16 != 0);
+      // folded-LayerNorm modes: A is the fp16 residual stream, so W' is stored in fp16 whatever the
+      // encoder's operand type (kind::f16 with A = f16, B = bf16 raises an illegal-instruction
+      // fault on sm_100a: measured, round 2); g.f16 then only selects the OUTPUT's 16-bit type
+      const uint32_t idesc = make_idesc_16(kBlockM * CTAS, BLOCK_N, mode_ln(MODE) || g.f16 != 0);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
@@ -349,7 +419,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;             // which column group of the BLOCK_N columns
     constexpr int kHalfCols = Epi::kColsPerWarp;
-    constexpr int kSlab = (MODE <= 1) ? 2048 : 4096;
+    constexpr int kSlab = mode_out16(MODE) ? 2048 : 4096;
     int it = 0;
     if constexpr (MODE == kBiasResidualF32Tma) {
       // ---- fp32 residual, in place, entirely through the TMA unit -------------------------
@@ -379,6 +449,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int row0 = (m_blk * CTAS + (int)cta_rank) * kBlockM + quarter * 32;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                (uint32_t)(as * BLOCK_N + half * kHalfCols);
+        float2 ssum = make_float2(0.f, 0.f), ssq = make_float2(0.f, 0.f);   // this row, this column group
 #pragma unroll 1
         for (int c = 0; c < kChunks; ++c, ++j) {
           if (lane == 0) {                       // prefetch the next chunk's residual tile
@@ -414,6 +485,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               h.w = pack_h2_sat(x3.x + (__uint_as_float(v[q * 8 + 6]) + b1.z),
                                 x3.y + (__uint_as_float(v[q * 8 + 7]) + b1.w));
               *px = h;
+              if (g.stats_out) {                       // sums of the stream as stored (rounded)
+                x0 = unpack_h2(h.x); x1 = unpack_h2(h.y); x2 = unpack_h2(h.z); x3 = unpack_h2(h.w);
+                ssum = fadd2(ssum, fadd2(fadd2(x0, x1), fadd2(x2, x3)));
+                ssq = ffma2(x0, x0, ssq); ssq = ffma2(x1, x1, ssq);
+                ssq = ffma2(x2, x2, ssq); ssq = ffma2(x3, x3, ssq);
+              }
             }
           } else {
             uint8_t* buf = xbuf + (j & 1) * 4096 + lane * 128;
@@ -436,6 +513,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_store_commit();
           }
         }
+        if (g.stats_out && row0 + lane < g.M)
+          g.stats_out[(size_t)(n_blk * Epi::kGroups + half) * g.stats_out_ld + (size_t)(row0 + lane)] =
+              make_float2(ssum.x + ssum.y, ssq.x + ssq.y);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -449,18 +529,44 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const int row0 = (m_blk * CTAS + (int)cta_rank) * kBlockM + quarter * 32;
+      float rstd = 1.f;
+      if constexpr (mode_ln(MODE)) {     // thread = accumulator row; rows past M are clipped by TMA
+        // fetched while this tile's MMAs are still running: the latency hides behind the wait
+        const int r = row0 + lane;
+        rstd = load_ln_rstd(g, r < g.M ? r : g.M - 1);
+      }
       mbar_wait(&tmem_full[as], aphase, 3);
       tcgen05_fence_after();
-      const int row0 = (m_blk * CTAS + (int)cta_rank) * kBlockM + quarter * 32;
       uint8_t* slab = slabs + (warp - 2) * kSlab;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                              (uint32_t)(as * BLOCK_N + half * kHalfCols);
+      float2 st[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) st[i] = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int c = 0; c < kHalfCols / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
         tmem_ld_wait();
-        epilogue_chunk<MODE>(v, g, &tmC, slab, row0, n_blk * BLOCK_N + half * kHalfCols + c * 32, lane);
+        epilogue_chunk<MODE>(v, g, &tmC, slab, row0, n_blk * BLOCK_N + half * kHalfCols + c * 32, lane,
+                             rstd, st);
+      }
+      if (MODE == kBiasResidualF32 && g.stats_out) {
+        // transposed phase: lanes 8 r' .. 8 r' + 7 hold the 4-column pieces of row i*4 + r'
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float s = st[i].x, q = st[i].y;
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+          }
+          const int r = row0 + i * 4 + (lane >> 3);
+          if ((lane & 7) == 0 && r < g.M)
+            g.stats_out[(size_t)(n_blk * Epi::kGroups + half) * g.stats_out_ld + (size_t)r] =
+                make_float2(s, q);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -470,7 +576,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     }
-    if (MODE <= 1 && lane == 0) tma_store_wait_read<0>();   // smem must outlive the last store
+    if (mode_out16(MODE) && lane == 0) tma_store_wait_read<0>();   // smem must outlive the last store
   }
 
   tcgen05_fence_before();

@@ -238,5 +238,8 @@ __host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, bool f16) {
   return f16 ? ((1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24))
              : make_idesc_bf16(M, N);
 }
+// (A = f16 with B = bf16, i.e. different format codes in [7,10) and [10,13), is rejected by the
+// hardware with an illegal-instruction fault -- tried in round 2 for the LayerNorm-folded GEMMs,
+// which therefore keep their weights in fp16 like the residual stream they read.)
 
 }  // namespace vpf

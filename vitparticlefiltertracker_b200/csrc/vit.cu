@@ -190,7 +190,7 @@ static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   CUtensorMap tmC = tmA;                       // modes 2 / 3 do not use it
-  if (MODE <= 1 || MODE == kBiasResidualF32Tma) {
+  if (mode_out16(MODE) || MODE == kBiasResidualF32Tma) {
     int rc = make_store_map(&tmC, g.out, (uint64_t)g.M, (uint64_t)g.N,
                             MODE == kBiasResidualF32Tma && !g.x16);
     if (rc) return rc;
@@ -218,6 +218,8 @@ static int launch_gemm_n(const CUtensorMap& a, const CUtensorMap& b, const GemmA
       return g.K <= 1536 ? launch_gemm_t<BLOCK_N, kBiasResidualF32Tma>(a, b, g, s)
                          : launch_gemm_t<BLOCK_N, kBiasResidualF32>(a, b, g, s);
     case kPatchEmbedF32: return launch_gemm_t<BLOCK_N, kPatchEmbedF32>(a, b, g, s);
+    case kLnBiasBf16: return launch_gemm_t<BLOCK_N, kLnBiasBf16>(a, b, g, s);
+    case kLnBiasGeluBf16: return launch_gemm_t<BLOCK_N, kLnBiasGeluBf16>(a, b, g, s);
   }
   set_error("gemm: unknown epilogue mode %d", mode);
   return VPF_ERR_INVALID;
@@ -439,6 +441,78 @@ static cudaError_t launch_layernorm(int blocks, cudaStream_t s, const float* x, 
                     out, rows, D, f16, x16);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row statistics of the fp16 residual stream for the LayerNorm-folded GEMMs: stats[row] = (mean,
+// 1/sqrt(var + 1e-6)), same arithmetic as layernorm16_kernel (fp32 mean, centred sum of squares).
+// Reads the stream once (2 B/element) and writes 8 B per row; used where no residual GEMM precedes
+// the LayerNorm (after the patch embedding) and as the A/B reference of the epilogue-fused sums.
+template <int NV>
+__global__ void __launch_bounds__(256, 4) rowstats16_kernel(const __half* __restrict__ x,
+                                                            float2* __restrict__ stats, int rows, int D) {
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int nvec = D >> 3;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const float inv_d = 1.0f / (float)D;
+  pdl_wait();
+  uint4 raw[NV];
+  auto load_row = [&](int r) {
+    const uint4* p = reinterpret_cast<const uint4*>(x + (size_t)r * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + 32 * i < nvec) raw[i] = p[lane + 32 * i];
+  };
+  if (row < rows) load_row(row);
+  for (; row < rows; row += warps) {
+    float2 v[NV][4];
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+        v[i][0] = unpack_h2(raw[i].x); v[i][1] = unpack_h2(raw[i].y);
+        v[i][2] = unpack_h2(raw[i].z); v[i][3] = unpack_h2(raw[i].w);
+        acc = fadd2(acc, fadd2(fadd2(v[i][0], v[i][1]), fadd2(v[i][2], v[i][3])));
+      }
+    }
+    if (row + warps < rows) load_row(row + warps);
+    const float mean = warp_sum(acc.x + acc.y) * inv_d;
+    const float2 nmean = make_float2(-mean, -mean);
+    float2 sq = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 c = fadd2(v[i][k], nmean);
+          sq = ffma2(c, c, sq);
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq.x + sq.y) * inv_d + 1e-6f);
+    if (lane == 0) stats[row] = make_float2(mean, rstd);
+  }
+}
+
+template <int NV>
+static cudaError_t launch_rowstats16_nv(cudaStream_t s, const __half* x, float2* stats, int rows, int D) {
+  int blocks = num_sms_any() * 4;
+  const int need = (rows + 7) / 8;
+  if (blocks > need) blocks = need;
+  return launch_pdl(pdl_for_rows(rows), rowstats16_kernel<NV>, dim3(blocks), dim3(256), 0, s, x, stats,
+                    rows, D);
+}
+static cudaError_t launch_rowstats16(cudaStream_t s, const void* x16, float2* stats, int rows, int D) {
+  const __half* x = reinterpret_cast<const __half*>(x16);
+  if (D <= 256) return launch_rowstats16_nv<1>(s, x, stats, rows, D);
+  if (D <= 512) return launch_rowstats16_nv<2>(s, x, stats, rows, D);
+  if (D <= 768) return launch_rowstats16_nv<3>(s, x, stats, rows, D);
+  return launch_rowstats16_nv<4>(s, x, stats, rows, D);
+}
+
+// column groups a residual GEMM with N = D splits a row into (its n-blocks x 2 epilogue halves)
+static int ln_stats_parts(int D) { const int bn = pick_block_n(D); return bn ? (D / bn) * 2 : 0; }
+
 // X[crop*T][:] = cls + pos[0]
 __global__ void cls_init_kernel(float* __restrict__ X, const float* __restrict__ cls,
                                 const float* __restrict__ pos, int n_crops, int D, int T, bool x16) {
@@ -628,6 +702,10 @@ struct LayerW {
   const float *ln1_g, *ln1_b, *qkv_b, *proj_b, *ln2_g, *ln2_b, *fc1_b, *fc2_b;
   const void *qkv_w, *proj_w, *fc1_w, *fc2_w;
   CUtensorMap m_qkv, m_proj, m_fc1, m_fc2;
+  // LayerNorm folded into qkv / fc1 (vpf_vit_set_ln_fold): W' = centred gamma (.) W, b' = b + W beta
+  const void *qkv_wf = nullptr, *fc1_wf = nullptr;
+  const float *qkv_bf = nullptr, *fc1_bf = nullptr;
+  CUtensorMap m_qkv_f, m_fc1_f;
 };
 
 }  // namespace vpf
@@ -657,6 +735,14 @@ struct vpf_vit {
   // CLS-only last block: strided CLS rows of Xn, compact [n][D] / [n][4D] operands
   CUtensorMap a_xn_cls, a_ocls, a_xnc, a_hc, m_kv_last, m_q_last;
   bool cls_prune = true;
+  // LayerNorm folded into the consuming GEMMs (fp16 residual stream + vpf_vit_set_ln_fold)
+  int ln_fold = 0;               // 0 off, 1 row statistics by rowstats16_kernel, 2 by the residual
+                                 // GEMMs' epilogues (kernel only after the patch embedding)
+  bool has_fold = false;
+  float2* stats_final = nullptr; // [max_rows] (mean, rstd)
+  float2* stats_part = nullptr;  // [parts][max_rows] (sum x, sum x^2)
+  bool parts_ready = false;      // stats_part describes the current X
+  CUtensorMap a_x, a_x_cls, m_kv_last_f, m_q_last_f;
   // optional in-step kernel timing (vpf_vit_set_timing): an event pair around every launch of a
   // forward, summed per kind by vpf_vit_timing
   bool timing = false;
@@ -748,7 +834,8 @@ size_t vpf_vit_workspace_bytes(const vpf_vit_config* cfg) {
   const size_t rows = (size_t)cfg->max_crops * tokens_of(cfg), D = cfg->dim;
   const size_t xsz = cfg->residual_dtype == VPF_RESIDUAL_F16 ? 2 : 4;
   return align_up(rows * D * xsz, 1024) + align_up(rows * D * 2, 1024) +
-         align_up(rows * 4 * D * 2, 1024) + cls_bytes(cfg->max_crops, D) + 1024;
+         align_up(rows * 4 * D * 2, 1024) + align_up(cls_bytes(cfg->max_crops, D), 1024) +
+         align_up(rows * sizeof(float2) * (size_t)(1 + ln_stats_parts(cfg->dim)), 1024) + 1024;
 }
 
 int vpf_vit_set_weights(vpf_vit* h, const void* const* p, int n) {
@@ -787,6 +874,44 @@ int vpf_vit_set_weights(vpf_vit* h, const void* const* p, int n) {
   return VPF_OK;
 }
 
+// VPF_LN_FOLD: 0 = keep the LayerNorm kernels, kernel = folded GEMMs with rowstats16_kernel before
+// each, anything else / unset = folded GEMMs fed by the residual epilogues' partial sums.
+static int ln_fold_mode() {
+  const char* e = getenv("VPF_LN_FOLD");
+  if (!e) return 2;
+  if (e[0] == '0') return 0;
+  return e[0] == 'k' ? 1 : 2;
+}
+
+int vpf_vit_set_ln_fold(vpf_vit* h, const void* const* p, int n) {
+  VPF_REQUIRE(h && p, "vpf_vit_set_ln_fold: null argument");
+  const int D = h->cfg.dim, L = h->cfg.depth;
+  VPF_REQUIRE(h->has_weights, "vpf_vit_set_ln_fold: call vpf_vit_set_weights first");
+  VPF_REQUIRE(h->x16, "vpf_vit_set_ln_fold: needs the fp16 residual stream (VPF_RESIDUAL_F16): the "
+                      "stream itself becomes the GEMM's A operand");
+  VPF_REQUIRE(n == 4 * L, "vpf_vit_set_ln_fold: expected %d pointers, got %d", 4 * L, n);
+  for (int i = 0; i < n; ++i) VPF_REQUIRE(p[i] != nullptr, "vpf_vit_set_ln_fold: pointer %d is null", i);
+  int k = 0, rc;
+  for (int l = 0; l < L; ++l) {
+    LayerW& w = h->layers[l];
+    w.qkv_wf = p[k++]; w.qkv_bf = (const float*)p[k++];
+    w.fc1_wf = p[k++]; w.fc1_bf = (const float*)p[k++];
+    if ((rc = make_map(&w.m_qkv_f, w.qkv_wf, 3 * D, D, pick_block_n(3 * D) / gemm_ctas()))) return rc;
+    if ((rc = make_map(&w.m_fc1_f, w.fc1_wf, 4 * D, D, pick_block_n(4 * D) / gemm_ctas()))) return rc;
+  }
+  {
+    const __nv_bfloat16* qkv = (const __nv_bfloat16*)h->layers[L - 1].qkv_wf;
+    if ((rc = make_map(&h->m_q_last_f, qkv, D, D, pick_block_n(D) / gemm_ctas()))) return rc;
+    if ((rc = make_map(&h->m_kv_last_f, qkv + (size_t)D * D, 2 * D, D,
+                       pick_block_n(2 * D) / gemm_ctas()))) return rc;
+  }
+  h->has_fold = true;
+  h->ln_fold = ln_fold_mode();
+  return VPF_OK;
+}
+
+int vpf_vit_ln_fold(const vpf_vit* h) { return h ? (h->has_fold ? h->ln_fold : 0) : 0; }
+
 int vpf_vit_set_workspace(vpf_vit* h, void* ws, size_t bytes) {
   VPF_REQUIRE(h && ws, "vpf_vit_set_workspace: null argument");
   VPF_REQUIRE(((uintptr_t)ws & 1023) == 0, "vpf_vit_set_workspace: workspace must be 1024-byte aligned");
@@ -797,7 +922,9 @@ int vpf_vit_set_workspace(vpf_vit* h, void* ws, size_t bytes) {
   h->X = (float*)b;            b += align_up(rows * D * (h->x16 ? 2 : 4), 1024);
   h->Xn = (__nv_bfloat16*)b;   b += align_up(rows * D * 2, 1024);
   h->big = (__nv_bfloat16*)b;  b += align_up(rows * 4 * D * 2, 1024);
-  h->cbuf = b;
+  h->cbuf = b;                 b += align_up(cls_bytes(h->cfg.max_crops, D), 1024);
+  h->stats_final = (float2*)b; b += rows * sizeof(float2);
+  h->stats_part = (float2*)b;
   h->has_ws = true;
   h->maps_for = -1;
   return VPF_OK;
@@ -806,8 +933,42 @@ int vpf_vit_set_workspace(vpf_vit* h, void* ws, size_t bytes) {
 int vpf_vit_launches(const vpf_vit* h) {
   if (!h) return 0;
   const int L = h->cfg.depth;
-  if (!h->cls_prune) return 2 /*cls, patch embed*/ + 7 * L + 1 /*final LN*/;
-  return 2 + 7 * (L - 1) + 10;
+  const int fold = h->has_fold ? h->ln_fold : 0;
+  // per full block: 2 LayerNorms + qkv, attention, proj, fc1, fc2; folded: the LayerNorms go
+  // (mode 2: one rowstats launch per forward; mode 1: one per former LayerNorm)
+  const int per_block = fold == 2 ? 5 : 7;
+  const int extra = fold == 2 ? 1 : 0;
+  if (!h->cls_prune) return 2 /*cls, patch embed*/ + per_block * L + extra + 1 /*final LN*/;
+  return 2 + per_block * (L - 1) + extra + (fold == 2 ? 9 : 10);
+}
+
+// ---- LayerNorm folded into qkv / fc1: where the row statistics come from ---------------------
+// Mode 2: the residual GEMM that last rewrote X left per-column-group partial sums (parts_ready);
+// otherwise (after the patch embedding, or mode 1) rowstats16_kernel makes final (mean, rstd).
+static int ensure_row_stats(vpf_vit* h, int M, cudaStream_t s) {
+  if (h->parts_ready) return VPF_OK;
+  VPF_TIMED(kTLayerNorm);
+  VPF_CUDA(launch_rowstats16(s, h->X, h->stats_final, M, h->cfg.dim));
+  return VPF_OK;
+}
+static void set_ln_stats(const vpf_vit* h, GemmArgs& g) {
+  if (h->parts_ready) {
+    g.stats = h->stats_part;
+    g.stats_parts = ln_stats_parts(h->cfg.dim);
+    g.stats_ld = (size_t)h->cfg.max_crops * h->tokens;
+  } else {
+    g.stats = h->stats_final;
+    g.stats_parts = 0;
+  }
+}
+// a residual GEMM over every row of X: in mode 2 its epilogue also produces the next statistics
+static void set_stats_out(vpf_vit* h, GemmArgs& g) {
+  const bool epi = h->has_fold && h->ln_fold == 2;
+  if (epi) {
+    g.stats_out = h->stats_part;
+    g.stats_out_ld = (size_t)h->cfg.max_crops * h->tokens;
+  }
+  h->parts_ready = epi;
 }
 
 // One full encoder block on every token row.
@@ -815,12 +976,20 @@ static int run_block(vpf_vit* h, const LayerW& w, int n, cudaStream_t s) {
   const int D = h->cfg.dim, H = h->cfg.heads, M = n * h->tokens;
   const int f16 = h->cfg.dtype == VPF_DTYPE_F16;
   const int ln_blocks = (M + 7) / 8;
+  const int fold = h->has_fold ? h->ln_fold : 0;
   int rc;
-  {
-    VPF_TIMED(kTLayerNorm);
-    VPF_CUDA(launch_layernorm<__nv_bfloat16>(ln_blocks, s, h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0, h->x16));
-  }
-  {
+  if (fold) {
+    if ((rc = ensure_row_stats(h, M, s))) return rc;
+    VPF_TIMED(kTQkv);
+    GemmArgs g{M, 3 * D, D, w.qkv_bf, h->big, nullptr};
+    g.f16 = f16;
+    set_ln_stats(h, g);
+    if ((rc = launch_gemm(h->a_x, w.m_qkv_f, g, kLnBiasBf16, s))) return rc;
+  } else {
+    {
+      VPF_TIMED(kTLayerNorm);
+      VPF_CUDA(launch_layernorm<__nv_bfloat16>(ln_blocks, s, h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0, h->x16));
+    }
     VPF_TIMED(kTQkv);
     GemmArgs g{M, 3 * D, D, w.qkv_b, h->big, nullptr};
       g.f16 = f16;
@@ -835,13 +1004,21 @@ static int run_block(vpf_vit* h, const LayerW& w, int n, cudaStream_t s) {
     GemmArgs g{M, D, D, w.proj_b, h->X, nullptr};
       g.f16 = f16;
       g.x16 = h->x16;
+    set_stats_out(h, g);
     if ((rc = launch_gemm(h->a_xn, w.m_proj, g, kBiasResidualF32, s))) return rc;
   }
-  {
-    VPF_TIMED(kTLayerNorm);
-    VPF_CUDA(launch_layernorm<__nv_bfloat16>(ln_blocks, s, h->X, D, w.ln2_g, w.ln2_b, h->Xn, M, D, f16 != 0, h->x16));
-  }
-  {
+  if (fold) {
+    if ((rc = ensure_row_stats(h, M, s))) return rc;
+    VPF_TIMED(kTFc1);
+    GemmArgs g{M, 4 * D, D, w.fc1_bf, h->big, nullptr};
+    g.f16 = f16;
+    set_ln_stats(h, g);
+    if ((rc = launch_gemm(h->a_x, w.m_fc1_f, g, kLnBiasGeluBf16, s))) return rc;
+  } else {
+    {
+      VPF_TIMED(kTLayerNorm);
+      VPF_CUDA(launch_layernorm<__nv_bfloat16>(ln_blocks, s, h->X, D, w.ln2_g, w.ln2_b, h->Xn, M, D, f16 != 0, h->x16));
+    }
     VPF_TIMED(kTFc1);
     GemmArgs g{M, 4 * D, D, w.fc1_b, h->big, nullptr};
       g.f16 = f16;
@@ -852,6 +1029,7 @@ static int run_block(vpf_vit* h, const LayerW& w, int n, cudaStream_t s) {
     GemmArgs g{M, D, 4 * D, w.fc2_b, h->X, nullptr};
       g.f16 = f16;
       g.x16 = h->x16;
+    set_stats_out(h, g);
     if ((rc = launch_gemm(h->a_big, w.m_fc2, g, kBiasResidualF32, s))) return rc;
   }
   return VPF_OK;
@@ -880,7 +1058,24 @@ static int run_last_block_cls(vpf_vit* h, const LayerW& w, int n, float* emb, cu
   const int f16 = h->cfg.dtype == VPF_DTYPE_F16;
   const ClsBufs c = cls_bufs(h, n);
   int rc;
+  if (h->has_fold && h->ln_fold)
+    if ((rc = ensure_row_stats(h, M, s))) return rc;
   VPF_TIMED(kTTail);
+  if (h->has_fold && h->ln_fold) {
+    {  // K, V for every token straight from the stream: rows [D, 3D) of the folded qkv weight
+      GemmArgs g{M, 2 * D, D, w.qkv_bf + D, h->big, nullptr};
+      g.f16 = f16;
+      set_ln_stats(h, g);
+      if ((rc = launch_gemm(h->a_x, h->m_kv_last_f, g, kLnBiasBf16, s))) return rc;
+    }
+    {  // Q for the CLS rows only (strided view of X; statistics of row crop*T)
+      GemmArgs g{n, D, D, w.qkv_bf, c.q, nullptr};
+      g.f16 = f16;
+      set_ln_stats(h, g);
+      g.stats_stride = T;
+      if ((rc = launch_gemm(h->a_x_cls, h->m_q_last_f, g, kLnBiasBf16, s))) return rc;
+    }
+  } else {
   VPF_CUDA(launch_layernorm<__nv_bfloat16>((M + 7) / 8, s, h->X, D, w.ln1_g, w.ln1_b, h->Xn, M, D, f16 != 0, h->x16));
   {  // K, V for every token: rows [D, 3D) of the fused qkv weight
     GemmArgs g{M, 2 * D, D, w.qkv_b + D, h->big, nullptr};
@@ -891,6 +1086,7 @@ static int run_last_block_cls(vpf_vit* h, const LayerW& w, int n, float* emb, cu
     GemmArgs g{n, D, D, w.qkv_b, c.q, nullptr};
       g.f16 = f16;
     if ((rc = launch_gemm(h->a_xn_cls, h->m_q_last, g, kBiasBf16, s))) return rc;
+  }
   }
   VPF_CUDA(launch_pdl(pdl_for_rows((long long)n * T), cls_attention_kernel, dim3((n * H + 7) / 8), dim3(256), 0, s, c.q, h->big, c.o,
                       n * H, H, f16 != 0, T));
@@ -931,6 +1127,10 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
   if (h->maps_for != n || h->maps_patches != patches) {
     if ((rc = make_map(&h->a_patches, patches, M0, 768, kBlockM))) return rc;
     if ((rc = make_map(&h->a_xn, h->Xn, M, D, kBlockM))) return rc;
+    if (h->x16) {               // the fp16 stream as a GEMM A operand (LayerNorm-folded GEMMs)
+      if ((rc = make_map(&h->a_x, h->X, M, D, kBlockM))) return rc;
+      if ((rc = make_map(&h->a_x_cls, h->X, n, D, kBlockM, (uint64_t)T * D))) return rc;
+    }
     if ((rc = make_map(&h->a_big, h->big, M, 4 * D, kBlockM))) return rc;
     if (T > 64) {             // tcgen05 attention (T <= 64: the warp-per-pair kernels need no map)
       if ((rc = make_qkv_map(&h->a_q, h->big, n, D, 128, T))) return rc;
@@ -946,6 +1146,7 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
   }
 
   if (h->timing) { h->ev_used = 0; h->ev_kind.clear(); }
+  h->parts_ready = false;
   {
     VPF_TIMED(kTPatch);
     VPF_CUDA(launch_pdl(pdl_for_rows((long long)n * T), cls_init_kernel, dim3((n * D + 255) / 256), dim3(256), 0, s, h->X, h->cls,
@@ -1004,6 +1205,54 @@ int vpf_gemm_bf16(const void* A, const void* W, const float* bias, void* out, co
   if (mode == kPatchEmbedF32) g.ppc = patches_per_crop;
   g.x16 = (mode >= kBiasResidualF32 && residual_dtype == VPF_RESIDUAL_F16) ? 1 : 0;
   return launch_gemm(ma, mb, g, mode, (cudaStream_t)stream);
+}
+
+int vpf_ln_stats_parts(int D) { return ln_stats_parts(D); }
+
+int vpf_rowstats16(const void* x16, float* stats, int rows, int D, void* stream) {
+  VPF_REQUIRE(x16 && stats && rows > 0 && D > 0 && D % 8 == 0 && D <= 1024,
+              "vpf_rowstats16: bad arguments (D multiple of 8, <= 1024)");
+  VPF_CUDA(launch_rowstats16((cudaStream_t)stream, x16, (float2*)stats, rows, D));
+  return VPF_OK;
+}
+
+int vpf_gemm_ln(const void* X16, const void* Wf, const float* bias_f, const float* stats,
+                int stats_parts, void* out, int M, int N, int K, int gelu, int dtype, void* stream) {
+  VPF_REQUIRE(X16 && Wf && bias_f && stats && out && M > 0 && N > 0 && K > 0,
+              "vpf_gemm_ln: bad arguments");
+  VPF_REQUIRE(K % kBlockK == 0, "vpf_gemm_ln: K=%d must be a multiple of 64", K);
+  VPF_REQUIRE(stats_parts >= 0 && stats_parts <= 16, "vpf_gemm_ln: stats_parts outside [0, 16]");
+  const int bn = pick_block_n(N);
+  if (!bn) { set_error("vpf_gemm_ln: N=%d must be a multiple of 128", N); return VPF_ERR_UNSUPPORTED; }
+  CUtensorMap ma, mb;
+  int rc;
+  if ((rc = make_map(&ma, X16, M, K, kBlockM))) return rc;
+  if ((rc = make_map(&mb, Wf, N, K, bn / gemm_ctas()))) return rc;
+  GemmArgs g{M, N, K, bias_f, out, nullptr};
+  g.f16 = dtype == VPF_DTYPE_F16;
+  g.stats = (const float2*)stats;
+  g.stats_parts = stats_parts;
+  g.stats_ld = (size_t)M;
+  return launch_gemm(ma, mb, g, gelu ? kLnBiasGeluBf16 : kLnBiasBf16, (cudaStream_t)stream);
+}
+
+int vpf_gemm_residual_stats(const void* A, const void* W, const float* bias, void* x16,
+                            float* stats_out, int M, int N, int K, int dtype, void* stream) {
+  VPF_REQUIRE(A && W && bias && x16 && stats_out && M > 0 && N > 0 && K > 0,
+              "vpf_gemm_residual_stats: bad arguments");
+  VPF_REQUIRE(K % kBlockK == 0, "vpf_gemm_residual_stats: K=%d must be a multiple of 64", K);
+  const int bn = pick_block_n(N);
+  if (!bn) { set_error("vpf_gemm_residual_stats: N=%d must be a multiple of 128", N); return VPF_ERR_UNSUPPORTED; }
+  CUtensorMap ma, mb;
+  int rc;
+  if ((rc = make_map(&ma, A, M, K, kBlockM))) return rc;
+  if ((rc = make_map(&mb, W, N, K, bn / gemm_ctas()))) return rc;
+  GemmArgs g{M, N, K, bias, x16, nullptr};
+  g.f16 = dtype == VPF_DTYPE_F16;
+  g.x16 = 1;
+  g.stats_out = (float2*)stats_out;
+  g.stats_out_ld = (size_t)M;
+  return launch_gemm(ma, mb, g, kBiasResidualF32, (cudaStream_t)stream);
 }
 
 int vpf_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows,

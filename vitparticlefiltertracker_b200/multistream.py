@@ -15,7 +15,8 @@ import torch
 from . import ops
 from .exchange import Exchange
 from .tracker import State
-from .vit_weights import VIT_CONFIGS, init_state_dict, load_checkpoint, pack_for_device
+from .vit_weights import (VIT_CONFIGS, init_state_dict, load_checkpoint, pack_for_device,
+                          pack_ln_fold)
 
 
 class MultiStreamTracker:
@@ -43,7 +44,9 @@ class MultiStreamTracker:
         self.encoder = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], self.S * self.n,
                                       pack_for_device(model, sd, crop_size=self.crop_size),
                                       device=self.device, crop_size=self.crop_size,
-                                      residual_dtype=residual_dtype)
+                                      residual_dtype=residual_dtype,
+                                      ln_fold=(pack_ln_fold(model, sd) if residual_dtype == torch.float16
+                                               else None))
         dev, S, n = self.device, self.S, self.n
         f32 = torch.float32
         self.particles = torch.zeros((S, 6, n), dtype=f32, device=dev)

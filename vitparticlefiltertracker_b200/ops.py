@@ -200,6 +200,61 @@ def layernorm(x, gamma, beta):
     return out
 
 
+def ln_stats_parts(D: int) -> int:
+    return _lib.load().vpf_ln_stats_parts(int(D))
+
+
+@_on_device
+def rowstats16(x16):
+    """(mean, 1/sqrt(var + 1e-6)) per row of an fp16 [rows][D] matrix -> f32 [rows][2]."""
+    _dev(x16, torch.float16)
+    rows, D = x16.shape
+    out = torch.empty((rows, 2), dtype=torch.float32, device=x16.device)
+    _lib.check(_lib.load().vpf_rowstats16(x16.data_ptr(), out.data_ptr(), rows, D, _stream()),
+               "vpf_rowstats16")
+    return out
+
+
+@_on_device
+def gemm_ln(x16, wf, bias_f, stats, gelu=False, out=None, dtype=torch.bfloat16):
+    """LayerNorm-folded GEMM: x16 fp16 [M][K] (the residual stream), wf fp16 [N][K] = gamma (.) W
+    with each row's mean subtracted, stats f32 [M][2] final (mean, rstd) or [P][M][2] partial (sum x, sum x^2) -> `dtype` [M][N]."""
+    _dev(x16, torch.float16)
+    M, K = x16.shape
+    N = wf.shape[0]
+    _dev(wf, torch.float16)
+    _dev(bias_f, torch.float32); _dev(stats, torch.float32)
+    parts = 0 if stats.dim() == 2 else stats.shape[0]
+    assert stats.shape[-2:] == (M, 2)
+    if out is None:
+        out = torch.empty((M, N), dtype=dtype, device=x16.device)
+    assert out.is_contiguous() and out.shape == (M, N)
+    _lib.check(_lib.load().vpf_gemm_ln(x16.data_ptr(), wf.data_ptr(), bias_f.data_ptr(),
+                                       stats.data_ptr(), parts, out.data_ptr(),
+                                       M, N, K, 1 if gelu else 0, _dtype_code(out.dtype), _stream()),
+               "vpf_gemm_ln")
+    return out
+
+
+@_on_device
+def gemm_residual_stats(a, w, bias, x16, out=None):
+    """x16 (fp16 [M][N], in place) += a @ w.T + bias; returns the partial row sums the epilogue
+    leaves for a following folded GEMM: f32 [P][M][2] = (sum x, sum x^2) per column group."""
+    M, K = a.shape
+    N = w.shape[0]
+    assert a.dtype == w.dtype and a.is_contiguous() and w.is_contiguous()
+    _dev(x16, torch.float16); _dev(bias, torch.float32)
+    P = ln_stats_parts(N)
+    if out is None:
+        out = torch.zeros((P, M, 2), dtype=torch.float32, device=a.device)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == (P, M, 2)
+    _lib.check(_lib.load().vpf_gemm_residual_stats(a.data_ptr(), w.data_ptr(), bias.data_ptr(),
+                                                   x16.data_ptr(), out.data_ptr(), M, N, K,
+                                                   _dtype_code(a.dtype), _stream()),
+               "vpf_gemm_residual_stats")
+    return out
+
+
 @_on_device
 def attention(qkv, n_crops, heads, tokens=TOKENS):
     _dev(qkv, torch.bfloat16)
@@ -270,7 +325,9 @@ class VitEncoder:
     """Owns the opaque vpf_vit handle, the packed device weights and the workspace tensor."""
 
     def __init__(self, dim, depth, heads, max_crops, packed_weights, device="cuda",
-                 dtype=torch.bfloat16, crop_size=CROP, residual_dtype=torch.float32):
+                 dtype=torch.bfloat16, crop_size=CROP, residual_dtype=torch.float32, ln_fold=None):
+        """`ln_fold`: the tensors of `vit_weights.pack_ln_fold` (fp16 residual stream only): the two
+        per-block LayerNorms are folded into the qkv / fc1 GEMMs, which then read the stream itself."""
         lib = _lib.load()
         self._lib = lib
         self.dim, self.depth, self.heads, self.max_crops = dim, depth, heads, max_crops
@@ -303,6 +360,19 @@ class VitEncoder:
         base = self.workspace.data_ptr()
         aligned = (base + 1023) // 1024 * 1024
         _lib.check(lib.vpf_vit_set_workspace(self._h, aligned, nbytes), "vpf_vit_set_workspace")
+        self.fold_weights = None
+        if ln_fold is not None:
+            if residual_dtype != torch.float16:
+                raise ValueError("ln_fold needs residual_dtype=torch.float16 (the stream is the A operand)")
+            if len(ln_fold) != 4 * depth or {t.dtype for t in ln_fold[0::2]} != {torch.float16}:
+                raise ValueError("ln_fold must be pack_ln_fold(model, sd): 4 tensors per block, W' in fp16")
+            self.fold_weights = [t.to(self.device).contiguous() for t in ln_fold]
+            arr = (C.c_void_p * len(self.fold_weights))(*[t.data_ptr() for t in self.fold_weights])
+            _lib.check(lib.vpf_vit_set_ln_fold(self._h, arr, len(self.fold_weights)),
+                       "vpf_vit_set_ln_fold")
+        #: 0 = LayerNorm kernels, 1 = folded with a row-statistics kernel, 2 = folded, statistics
+        #: from the residual GEMMs' epilogues (env VPF_LN_FOLD chooses; default 2 when folded)
+        self.ln_fold = lib.vpf_vit_ln_fold(self._h)
         self.launches = lib.vpf_vit_launches(self._h)
 
     def forward(self, patches, n_crops, emb=None):

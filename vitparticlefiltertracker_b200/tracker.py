@@ -29,7 +29,8 @@ import torch
 
 from . import ops
 from .exchange import Exchange, shard_range, shard_sizes
-from .vit_weights import VIT_CONFIGS, init_state_dict, load_checkpoint, pack_for_device
+from .vit_weights import (VIT_CONFIGS, init_state_dict, load_checkpoint, pack_for_device,
+                          pack_ln_fold)
 
 
 class _Stage:
@@ -77,7 +78,7 @@ class Tracker:
                  dtype=torch.bfloat16, tau=0.1, sigma_pos=None, sigma_vel=None, sigma_scale=0.01,
                  sigma_init=None, state_dict=None, process_group=None, stream_id=0,
                  encoder=None, cuda_graph=False, crop_size=224, residual_dtype=torch.float16,
-                 shards=None):
+                 shards=None, ln_fold=None):
         if not torch.cuda.is_available():
             raise RuntimeError("Tracker needs a CUDA device: the hot path has no CPU fallback")
         if dtype not in (torch.bfloat16, torch.float16):
@@ -90,6 +91,11 @@ class Tracker:
         # (profiles/parity_r02.json: it adds ~2 % to the bf16 operands' own distance from the
         # oracle).  torch.float32 restores the round-1 behaviour.
         self.residual_dtype = residual_dtype
+        # LayerNorm folded into the qkv / fc1 GEMMs (they read the fp16 stream itself; the row
+        # statistics come out of the proj / fc2 epilogues): default whenever the stream is fp16.
+        self.ln_fold = (residual_dtype == torch.float16) if ln_fold is None else bool(ln_fold)
+        if self.ln_fold and residual_dtype != torch.float16:
+            raise ValueError("ln_fold needs residual_dtype=torch.float16")
         # 224 = the oracle's default; a smaller multiple of 16 is the "native-resolution crops"
         # option of SURVEY.md section 8f-2 (e.g. 64 -> 17 tokens per particle instead of 197)
         self.crop_size = int(crop_size)
@@ -127,7 +133,8 @@ class Tracker:
             encoder = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], self.n,
                                      pack_for_device(model, sd, dtype, self.crop_size),
                                      device=self.device, dtype=dtype, crop_size=self.crop_size,
-                                     residual_dtype=residual_dtype)
+                                     residual_dtype=residual_dtype,
+                                     ln_fold=pack_ln_fold(model, sd, dtype) if self.ln_fold else None)
         assert encoder.max_crops >= self.n and encoder.dtype == dtype
         assert encoder.crop_size == self.crop_size
         self.encoder = encoder

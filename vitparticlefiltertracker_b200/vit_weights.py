@@ -144,3 +144,36 @@ def pack_for_device(model: str, sd: dict, dtype=torch.bfloat16, crop_size: int =
             out.append(bf(t) if (key.endswith("weight") and t.dim() == 2) else f32(t))
     out += [f32(sd["norm.weight"]), f32(sd["norm.bias"])]
     return out
+
+
+def pack_ln_fold(model: str, sd: dict, dtype=torch.bfloat16, storage=torch.float16) -> list:
+    """LayerNorm folded into the two GEMMs that consume it (include/vpf.h `vpf_vit_set_ln_fold`):
+
+        LN(x) W^T + b = r (x W'^T) + b',   W'_jk = gamma_k W_jk - mean_k(gamma_k W_jk),   b' = b + W beta
+
+    with r the row's 1/sqrt(var + eps): subtracting each weight row's mean over k makes x W'^T equal
+    (x - mean(x)) (gamma (.) W)^T, so the GEMM's epilogue needs only r.  Per block four CPU tensors:
+    qkv W', b' (fp32), fc1 W', b'.  Formed in fp64 from the fp32 master weights.
+
+    W' is rounded to the encoder's operand type `dtype` and then STORED in fp16 (exact for bf16
+    values above fp16's subnormal range): the folded GEMMs read the fp16 residual stream as A, and
+    tcgen05's kind::f16 wants one 16-bit type for both operands (A = f16 with B = bf16 faults on
+    sm_100a).  Keeping bf16's 8 significant bits inside the fp16 container is deliberate: the step
+    is power-limited and the multipliers' switching grows with the operands' mantissa width --
+    measured on one B200, alternating: 146.5 / 147.2 ms per step against 150.8 / 150.8 ms with full
+    fp16 weights (155.3 / 155.4 ms with separate LayerNorm kernels).
+
+    The rounding leaves a row sum eps_j = sum_k W'_jk of ~3e-2 |w| (bf16; 4e-3 |w| fp16) instead of
+    0, i.e. an output error of r mean(x) eps_j ~ 1e-3 (mean(x) / std(x)) relative to the output's
+    scale -- a fraction of the 16-bit output rounding for the |mean| < std rows of a ViT stream.
+    (`storage=torch.float32, dtype=torch.float32` gives the unrounded algebra for host tests.)"""
+    out = []
+    for i in range(VIT_CONFIGS[model]["depth"]):
+        k = _block_keys(i)
+        for g_key, b_key, w_key, bias_key in ((k[0], k[1], k[2], k[3]), (k[6], k[7], k[8], k[9])):
+            gamma, beta = sd[g_key].detach().double(), sd[b_key].detach().double()
+            w, bias = sd[w_key].detach().double(), sd[bias_key].detach().double()
+            wf = w * gamma[None, :]
+            wf = (wf - wf.mean(dim=1, keepdim=True)).to(torch.float32).to(dtype).to(torch.float32)
+            out += [wf.to(storage).contiguous(), (bias + w @ beta).to(torch.float32).contiguous()]
+    return out
