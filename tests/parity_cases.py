@@ -19,11 +19,14 @@ import torch
 #:   ess   |ESS_gpu / ESS_oracle - 1|        bbox  max |bbox_gpu - bbox_oracle| in pixels
 #:   emb   relative L2 distance of the embeddings
 TOL = {
-    # achieved (profiles/parity_r02.json, worst of four cases x two residual types):
-    #   bf16: dcos 2.2e-3, relw 1.6e-2, ess 6.3e-3, bbox 0.027 px, emb 7.9e-3
-    #   fp16: dcos 4.1e-4, relw 3.8e-3, ess 8.9e-4, bbox 0.004 px, emb 1.7e-3
+    # achieved (profiles/parity_r02.json, worst of four cases x two residual types, LayerNorm
+    # folded into qkv / fc1 where the stream is fp16):
+    #   bf16: dcos 1.8e-3, relw 1.5e-2, ess 3.0e-3, bbox 0.026 px, emb 7.7e-3
+    #   fp16: dcos 6.8e-4, relw 4.4e-3, ess 7.6e-4, bbox 0.005 px, emb 1.6e-3
+    # (dcos / relw are maxima of rounding noise over a few hundred particles: +-50 % between builds
+    # with the same embedding error -- BASELINE.md section 5.1)
     "bf16": dict(dcos=3e-3, relw=3e-2, ess=0.01, bbox=0.05, emb=1e-2),
-    "fp16": dict(dcos=5e-4, relw=5e-3, ess=0.002, bbox=0.01, emb=2e-3),
+    "fp16": dict(dcos=1e-3, relw=7e-3, ess=0.002, bbox=0.01, emb=2e-3),
 }
 
 #: (name, model, particles, frames, clip) -- clip = (kind, H, W, target)

@@ -111,20 +111,20 @@ def test_residual_epilogue_partial_sums(M, N, K):
     assert _rel(o_parts, o_final) < 1e-4            # at most an output ulp here and there
 
 
-def _encoders(model, n, S, sd, dev, modes):
+def _encoders(model, n, S, sd, dev, modes, dtype=torch.bfloat16):
     from vitparticlefiltertracker_b200 import ops, pack_for_device
     from vitparticlefiltertracker_b200.vit_weights import pack_ln_fold
     cfg = VIT_CONFIGS[model]
-    packed = pack_for_device(model, sd, crop_size=S)
+    packed = pack_for_device(model, sd, dtype, crop_size=S)
     encs = {}
     for name, env in modes.items():
         old = os.environ.get("VPF_LN_FOLD")
         if env is not None:
             os.environ["VPF_LN_FOLD"] = env
         try:
-            encs[name] = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], n, packed, dev, crop_size=S,
-                                        residual_dtype=torch.float16,
-                                        ln_fold=None if name == "plain" else pack_ln_fold(model, sd))
+            encs[name] = ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], n, packed, dev, dtype=dtype,
+                                        crop_size=S, residual_dtype=torch.float16,
+                                        ln_fold=None if name == "plain" else pack_ln_fold(model, sd, dtype))
         finally:
             os.environ.pop("VPF_LN_FOLD", None)
             if old is not None:
@@ -132,10 +132,12 @@ def _encoders(model, n, S, sd, dev, modes):
     return encs
 
 
-@pytest.mark.parametrize("model,n,S", [("vit_tiny_patch16_224", 9, 224), ("vit_base_patch16_224", 3, 224),
-                                       ("vit_small_patch16_224", 4, 224),
-                                       ("vit_tiny_patch16_224", 6, 64), ("vit_large_patch16_224", 2, 224)])
-def test_encoder_ln_fold_matches_oracle(model, n, S):
+@pytest.mark.parametrize("model,n,S,dtype", [
+    ("vit_tiny_patch16_224", 9, 224, torch.bfloat16), ("vit_base_patch16_224", 3, 224, torch.bfloat16),
+    ("vit_small_patch16_224", 4, 224, torch.bfloat16), ("vit_tiny_patch16_224", 6, 64, torch.bfloat16),
+    ("vit_large_patch16_224", 2, 224, torch.bfloat16),
+    ("vit_tiny_patch16_224", 24, 224, torch.float16), ("vit_base_patch16_224", 3, 224, torch.float16)])
+def test_encoder_ln_fold_matches_oracle(model, n, S, dtype):
     dev = cuda()
     sd = init_vit_weights(model)
     g = torch.Generator().manual_seed(11)
@@ -150,16 +152,16 @@ def test_encoder_ln_fold_matches_oracle(model, n, S):
                       rng.uniform(30, 90, n), rng.uniform(30, 90, n)], 1).astype(np.float32)
     crops = crop_resize(frame, boxes, size=S)
     want = torch.from_numpy(vit_forward(crops, sd, model))
-    patches = torch.from_numpy(patchify(crops)).to(torch.bfloat16).to(dev)
-    encs = _encoders(model, n, S, sd, dev, {"plain": None, "kernel": "kernel", "epilogue": None})
+    patches = torch.from_numpy(patchify(crops)).to(dtype).to(dev)
+    encs = _encoders(model, n, S, sd, dev, {"plain": None, "kernel": "kernel", "epilogue": None}, dtype)
     assert (encs["plain"].ln_fold, encs["kernel"].ln_fold, encs["epilogue"].ln_fold) == (0, 1, 2)
     rel = {}
     for name, enc in encs.items():
         out = enc.forward(patches, n).cpu()
         rel[name] = _rel(out, want)
         cos = torch.nn.functional.cosine_similarity(out, want, dim=1).min()
-        print(f"{model} S={S} LayerNorm {name}: rel-L2 {rel[name]:.3e}, min cos {cos:.6f}")
-        assert rel[name] < 1.5e-2 and cos > 1 - 1e-3
+        print(f"{model} S={S} {dtype} LayerNorm {name}: rel-L2 {rel[name]:.3e}, min cos {cos:.7f}")
+        assert rel[name] < (1.5e-2 if dtype == torch.bfloat16 else 3e-3) and cos > 1 - 1e-3
     # folding removes the 16-bit rounding of the normalised activation: never further from the
     # oracle than the LayerNorm kernels by more than noise
     assert rel["kernel"] < rel["plain"] * 1.15 + 3e-4

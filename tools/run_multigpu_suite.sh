@@ -1,27 +1,32 @@
 #!/bin/bash
-# Multi-GPU measurements of one round, run on an N-GPU box (N = first argument, default 8):
-#   real-NCCL bit-parity (equal / uneven shards, eager / captured graph), the weak-scaling bench
-#   with per-rank timing (equal and balanced shards, eager and graph), BASELINE configs[3] / [4]
-#   as named, and the tracker-on-a-non-current-device test.  Everything lands in gpurun_out/.
-N=${1:-8}
+# Multi-GPU measurements of one round on ONE 8-GPU box, packed into waves so the box time (charged
+# 8x) stays short: runs that need fewer than 8 GPUs share a wave on disjoint GPU sets
+# (CUDA_VISIBLE_DEVICES; power and clocks are per GPU).  Everything lands in gpurun_out/mg_*.
+#   real-NCCL bit-parity at 8 GPUs (uneven shards, captured graph), the weak-scaling bench with
+#   per-rank timing at N = 8 (equal and balanced shards) / 4 / 2 / 1, BASELINE configs[3] at 8 / 4 / 2 GPUs and configs[4] at 8.
 mkdir -p gpurun_out
-TR="timeout 170 python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 port=29510
-run() {  # name, nproc, command...
-  local name=$1 np=$2; shift 2
+launch() {  # name, gpu list, nproc, command...   (background; wait with `wait`)
+  local name=$1 gpus=$2 np=$3; shift 3
   port=$((port + 1))
-  echo "=== $name (nproc $np)"
-  $TR --nproc-per-node $np --master-port $port "$@" > gpurun_out/mg_${name}.json 2> gpurun_out/mg_${name}.err
-  echo "rc=$? $(tail -c 400 gpurun_out/mg_${name}.json)"
+  ( CUDA_VISIBLE_DEVICES=$gpus timeout 240 python -m torch.distributed.run --nnodes=1 \
+      --master-addr 127.0.0.1 --master-port $port --nproc-per-node $np "$@" \
+      > gpurun_out/mg_${name}.json 2> gpurun_out/mg_${name}.err
+    echo "=== $name (GPUs $gpus) rc=$? $(tail -c 300 gpurun_out/mg_${name}.json)" ) &
 }
-if [ "$N" -lt 8 ]; then run parity_${N}gpu $N tools/check_multigpu.py; fi
-VPF_CHECK_SHARDS=uneven VPF_CHECK_GRAPH=1 run parity_${N}gpu_uneven_graph $N tools/check_multigpu.py
-run bench_${N}gpu_equal $N bench.py --gpus $N --steps 8 --warmup 3
-run bench_${N}gpu_balanced $N bench.py --gpus $N --steps 8 --warmup 3 --shards balanced
-if [ "$N" -lt 8 ]; then run bench_${N}gpu_graph $N bench.py --gpus $N --steps 8 --warmup 3 --graph; fi
-if [ "$N" -ge 8 ]; then
-  for n in 2 4 8; do run cfg3_${n}gpu $n tools/bench_configs_multigpu.py --config cfg3 --steps 3 --warmup 2; done
-  run cfg4_8gpu 8 tools/bench_configs_multigpu.py --config cfg4 --steps 3 --warmup 2
-fi
-timeout 120 python -m pytest tests/test_gpu_multirank.py -q -k non_current -p no:cacheprovider 2>&1 | tail -3
+ALL=0,1,2,3,4,5,6,7
+date +%T
+launch bench_8gpu_equal $ALL 8 bench.py --gpus 8 --steps 8 --warmup 3; wait; date +%T
+launch bench_8gpu_balanced $ALL 8 bench.py --gpus 8 --steps 8 --warmup 3 --shards balanced; wait; date +%T
+VPF_CHECK_SHARDS=uneven VPF_CHECK_GRAPH=1 launch parity_8gpu_uneven_graph $ALL 8 tools/check_multigpu.py; wait; date +%T
+launch cfg3_8gpu $ALL 8 tools/bench_configs_multigpu.py --config cfg3 --steps 3 --warmup 2; wait; date +%T
+launch cfg4_8gpu $ALL 8 tools/bench_configs_multigpu.py --config cfg4 --steps 3 --warmup 2; wait; date +%T
+launch bench_4gpu_equal 0,1,2,3 4 bench.py --gpus 4 --steps 8 --warmup 3
+launch cfg3_4gpu 4,5,6,7 4 tools/bench_configs_multigpu.py --config cfg3 --steps 3 --warmup 2; wait; date +%T
+launch bench_2gpu_equal 0,1 2 bench.py --gpus 2 --steps 8 --warmup 3
+launch cfg3_2gpu 2,3 2 tools/bench_configs_multigpu.py --config cfg3 --steps 3 --warmup 2
+# the same single-GPU bench on four different GPUs of the box: the GPU-to-GPU spread that the
+# per-frame all-gather turns into waiting at N > 1
+for g in 4 5 6 7; do launch bench_1gpu_dev$g $g 1 bench.py --gpus 1 --steps 8 --warmup 3 --no-extras; done
+wait; date +%T
 nvidia-smi --query-gpu=index,clocks.sm,power.draw,clocks_event_reasons.sw_power_cap --format=csv > gpurun_out/mg_smi.csv
