@@ -9,7 +9,7 @@ port=29510
 launch() {  # name, gpu list, nproc, command...   (background; wait with `wait`)
   local name=$1 gpus=$2 np=$3; shift 3
   port=$((port + 1))
-  ( CUDA_VISIBLE_DEVICES=$gpus timeout 240 python -m torch.distributed.run --nnodes=1 \
+  ( CUDA_VISIBLE_DEVICES=$gpus timeout 120 python -m torch.distributed.run --nnodes=1 \
       --master-addr 127.0.0.1 --master-port $port --nproc-per-node $np "$@" \
       > gpurun_out/mg_${name}.json 2> gpurun_out/mg_${name}.err
     echo "=== $name (GPUs $gpus) rc=$? $(tail -c 300 gpurun_out/mg_${name}.json)" ) &
