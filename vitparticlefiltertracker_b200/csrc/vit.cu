@@ -101,6 +101,26 @@ static int make_store_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint
   return VPF_OK;
 }
 
+// The epilogue's tensor map depends only on (pointer, rows, cols, element type): encoded once and
+// kept -- a frame re-uses the same ~10 output buffers for its ~60 GEMM launches, and each encode is
+// a driver call on the host's critical path (visible at ViT-Ti scale, where a frame is 2 ms).
+static int cached_store_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, bool f32) {
+  struct Entry { const void* ptr; uint64_t rows, cols; bool f32; CUtensorMap map; };
+  static std::mutex mu;
+  static std::vector<Entry> cache;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Entry& e : cache)
+      if (e.ptr == ptr && e.rows == rows && e.cols == cols && e.f32 == f32) { *map = e.map; return VPF_OK; }
+  }
+  int rc = make_store_map(map, ptr, rows, cols, f32);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache.size() >= 256) cache.clear();
+  cache.push_back(Entry{ptr, rows, cols, f32, *map});
+  return VPF_OK;
+}
+
 static int num_sms();
 static int num_sms_any() { return num_sms(); }
 
@@ -191,8 +211,8 @@ static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   cfg.numAttrs = 2;
   CUtensorMap tmC = tmA;                       // modes 2 / 3 do not use it
   if (mode_out16(MODE) || MODE == kBiasResidualF32Tma) {
-    int rc = make_store_map(&tmC, g.out, (uint64_t)g.M, (uint64_t)g.N,
-                            MODE == kBiasResidualF32Tma && !g.x16);
+    int rc = cached_store_map(&tmC, g.out, (uint64_t)g.M, (uint64_t)g.N,
+                              MODE == kBiasResidualF32Tma && !g.x16);
     if (rc) return rc;
   }
   VPF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g));
