@@ -104,7 +104,18 @@ __device__ __forceinline__ uint16_t pack16(float a, bool f16) {
 
 // ---- 16-bit (fp16) residual stream option: saturating conversions ------------------------------
 // two floats -> packed fp16x2 (first element in the low half), overflow clamps to +-65504
+// -DVPF_EXPERIMENT_STREAM_BF16=1 (A/B builds only, tools/ab_bench.sh): the stream keeps bf16's 8
+// significant bits inside its fp16 container -- a measurement of what the mantissa width of the
+// folded GEMMs' A operand costs under the power cap, NOT a shippable mode (it coarsens the
+// residual stream itself).
+#ifndef VPF_EXPERIMENT_STREAM_BF16
+#define VPF_EXPERIMENT_STREAM_BF16 0
+#endif
 __device__ __forceinline__ uint32_t pack_h2_sat(float first, float second) {
+#if VPF_EXPERIMENT_STREAM_BF16
+  first = __bfloat162float(__float2bfloat16_rn(first));
+  second = __bfloat162float(__float2bfloat16_rn(second));
+#endif
   uint32_t d;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first));
   return d;
