@@ -1,7 +1,7 @@
 """Turns the raw ncu artefacts brought back in gpurun_out/ into the committed summaries under
 profiles/ (run here, no GPU needed):
 
-    python tools/summarize_ncu.py gpurun_out/launches_r01d.csv gpurun_out/prof_gemm_r01d.ncu-rep
+    python tools/summarize_ncu.py gpurun_out/launches.csv gpurun_out/prof_gemm.ncu-rep
 """
 import collections
 import csv
