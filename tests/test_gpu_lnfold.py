@@ -181,3 +181,75 @@ def test_encoder_ln_fold_is_batch_invariant():
     for lo, hi in ((0, 1), (5, 18), (30, 37)):
         part = enc.forward(patches[lo * 196:hi * 196].contiguous(), hi - lo)
         assert torch.equal(part, full[lo:hi])
+
+
+def test_ln_fold_writers_stay_inside_their_buffers():
+    """compute-sanitizer is closed on this pool: the new writers (row statistics, the residual
+    epilogues' partial sums, the folded GEMM's TMA stores) get sentinel-filled arenas around their
+    outputs, ragged row counts, and both epilogue flavours of the residual GEMM."""
+    from vitparticlefiltertracker_b200 import _lib, ops
+    dev = cuda()
+    lib = _lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    PAD = 2048
+
+    def arena(n_elems, dtype, fill):
+        a = torch.full((n_elems + 2 * PAD,), fill, dtype=dtype, device=dev)
+        return a, a[PAD:PAD + n_elems]
+
+    def intact(a, n_elems, fill):
+        return bool((a[:PAD] == fill).all()) and bool((a[PAD + n_elems:] == fill).all())
+
+    g = torch.Generator().manual_seed(9)
+    for M, D in ((1, 192), (129, 192), (333, 384), (257, 768), (700, 1024)):
+        x = _stream_like(M, D, g, dev)
+        # row statistics kernel
+        a, st = arena(M * 2, torch.float32, -7.0)
+        _lib.check(lib.vpf_rowstats16(x.data_ptr(), st.data_ptr(), M, D, stream), "vpf_rowstats16")
+        torch.cuda.synchronize()
+        assert intact(a, M * 2, -7.0) and bool((st.view(M, 2)[:, 1] > 0).all()), (M, D)
+        # residual GEMM + partial sums: K = D (TMA epilogue) and K = 4 D (register-staged epilogue)
+        P = ops.ln_stats_parts(D)
+        for K in (D, 4 * D):
+            act = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+            w = (torch.randn(D, K, generator=g) * 0.03).to(torch.bfloat16).to(dev)
+            bias = torch.zeros(D, device=dev)
+            ax, xs = arena(M * D, torch.float16, 77.0)
+            xs.view(M, D).copy_(x)
+            ap, parts = arena(P * M * 2, torch.float32, -3.0)
+            _lib.check(lib.vpf_gemm_residual_stats(act.data_ptr(), w.data_ptr(), bias.data_ptr(),
+                                                   xs.data_ptr(), parts.data_ptr(), M, D, K,
+                                                   _lib.DTYPE_BF16, stream), "vpf_gemm_residual_stats")
+            torch.cuda.synchronize()
+            assert intact(ax, M * D, 77.0) and intact(ap, P * M * 2, -3.0), (M, D, K)
+            assert bool((parts.view(P, M, 2)[:, :, 1] >= 0).all()), (M, D, K)     # every slot written
+            # folded GEMM reading those sums: ragged M, output fenced
+            N = 256
+            wq = (torch.randn(N, D, generator=g) * 0.05).to(torch.float16).to(dev)
+            ao, out = arena(M * N, torch.bfloat16, 1000.0)
+            _lib.check(lib.vpf_gemm_ln(xs.data_ptr(), wq.data_ptr(), torch.zeros(N, device=dev).data_ptr(),
+                                       parts.data_ptr(), P, out.data_ptr(), M, N, D, 1,
+                                       _lib.DTYPE_BF16, stream), "vpf_gemm_ln")
+            torch.cuda.synchronize()
+            assert intact(ao, M * N, 1000.0), (M, D, K)
+            assert bool((out.float().abs() < 500.0).all()), (M, D, K)            # every element written
+
+
+def test_ln_fold_argument_checks():
+    from vitparticlefiltertracker_b200 import ops, pack_for_device
+    from vitparticlefiltertracker_b200.vit_weights import pack_ln_fold
+    dev = cuda()
+    model = "vit_tiny_patch16_224"
+    cfg = VIT_CONFIGS[model]
+    sd = init_vit_weights(model)
+    packed = pack_for_device(model, sd)
+    with pytest.raises(ValueError):        # the fp32 stream cannot be a GEMM operand
+        ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], 2, packed, dev, ln_fold=pack_ln_fold(model, sd))
+    with pytest.raises(ValueError):        # wrong number of tensors
+        ops.VitEncoder(cfg["dim"], cfg["depth"], cfg["heads"], 2, packed, dev, residual_dtype=torch.float16,
+                       ln_fold=pack_ln_fold(model, sd)[:-1])
+    from vitparticlefiltertracker_b200 import Tracker
+    with pytest.raises(ValueError):
+        Tracker(model, 8, residual_dtype=torch.float32, ln_fold=True)
+    assert Tracker(model, 8, ln_fold=False).encoder.ln_fold == 0
+    assert Tracker(model, 8).encoder.ln_fold == 2
