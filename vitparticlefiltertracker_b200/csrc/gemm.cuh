@@ -357,7 +357,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int a_row = (m_blk * CTAS + (int)cta_rank) * kBlockM;
         const int b_row = n_blk * BLOCK_N + (int)cta_rank * Cfg::kBRows;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1, 0);
+          mbar_wait<true>(&empty_bar[stage], phase ^ 1, 0);
           uint8_t* sa = tiles + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           if (CTAS == 2) {
@@ -387,11 +387,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[as], aphase ^ 1, 1);   // epilogues have drained this accumulator
+        mbar_wait<true>(&tmem_empty[as], aphase ^ 1, 1);   // epilogues have drained this accumulator
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase, 2);      // TMA bytes (of both CTAs) have landed
+          mbar_wait<true>(&full_bar[stage], phase, 2);      // TMA bytes (of both CTAs) have landed
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
           const uint64_t adesc = make_smem_desc_k_sw128(sa);
@@ -444,7 +444,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tmem_full[as], aphase, 3);
+        mbar_wait<true>(&tmem_full[as], aphase, 3);
         tcgen05_fence_after();
         const int row0 = (m_blk * CTAS + (int)cta_rank) * kBlockM + quarter * 32;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
@@ -466,7 +466,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tmem_ld_wait();
           const int col = n_blk * BLOCK_N + half * kHalfCols + c * 32;
           const float4* b4 = reinterpret_cast<const float4*>(g.bias + col);
-          mbar_wait(&xbar[j & 1], (j >> 1) & 1, 4);
+          mbar_wait<true>(&xbar[j & 1], (j >> 1) & 1, 4);
           if (x16) {
             // row = 64 B: 16-byte piece q (8 halves) at lane*64 + ((q ^ ((lane>>1)&3)) << 4)
             uint8_t* buf = xbuf + (j & 1) * 4096 + lane * 64;
@@ -536,7 +536,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int r = row0 + lane;
         rstd = load_ln_rstd(g, r < g.M ? r : g.M - 1);
       }
-      mbar_wait(&tmem_full[as], aphase, 3);
+      mbar_wait<true>(&tmem_full[as], aphase, 3);
       tcgen05_fence_after();
       uint8_t* slab = slabs + (warp - 2) * kSlab;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +

@@ -28,17 +28,40 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Potentially-blocking test of a phase.  PARK = true adds a suspend-time hint: ptxas then parks the
+// warp (NANOSLEEP.SYNCS, woken by the barrier) instead of re-polling at the system default rate.
+// Measured (round 2, same-box alternating A/B, profiles/ab_mbar_suspend_r02.txt): the GEMMs' many
+// waiting warps (16 epilogue warps per CTA idle half of every tile) stop competing with the MMA
+// and TMA threads for issue slots -- isolated GEMMs 6-8 % faster, fc2 in-step 34.5 -> 32.2 ms --
+// but the attention kernel, whose warps hand work to each other every few hundred cycles, loses
+// 5 % to the wake-up latency.  So: parked waits in gemm.cuh, plain ones in the attention kernels.
+#ifndef VPF_MBAR_SUSPEND_NS
+#define VPF_MBAR_SUSPEND_NS 1000000
+#endif
+template <bool PARK>
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
+  if constexpr (PARK && VPF_MBAR_SUSPEND_NS > 0) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)VPF_MBAR_SUSPEND_NS)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
   return ok != 0;
 }
 // Bounded wait: a protocol bug must fail loudly (trap -> launch error), never hang the GPU.
@@ -47,10 +70,11 @@ __device__ __noinline__ void mbar_timeout(int role, uint32_t parity) {
          parity);
   __trap();
 }
+template <bool PARK = false>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int role) {
-  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait<PARK>(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait<PARK>(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) mbar_timeout(role, parity);  // ~2 s
   }
 }
