@@ -45,6 +45,29 @@ def test_gemm_gelu():
     assert ((out - ref).abs() <= 0.01 * ref.abs() + 2e-3).all() and _rel(out, ref) < 4e-3
 
 
+def test_gelu_epilogue_accuracy_against_fp64_erf_gelu():
+    """The epilogue's GELU alone (identity weights, zero bias): every output within the bf16
+    rounding of the exact erf-GELU plus the stated error of the tanh form (2.5e-5 formula error,
+    2^-11 relative on tanh.approx => <= 2.4e-4 |x|); rms error far below the rounding's."""
+    from vitparticlefiltertracker_b200 import ops
+    dev = cuda()
+    g = torch.Generator(device="cpu").manual_seed(4)
+    M, N = 4096, 128
+    x = torch.cat([torch.randn(M - 64, N, generator=g) * 1.5,
+                   torch.linspace(-9, 9, 64 * N).view(64, N)]).to(torch.bfloat16)
+    out = ops.gemm_bf16(x.to(dev), torch.eye(N).to(torch.bfloat16).to(dev), torch.zeros(N, device=dev), 1)
+    xd = x.double()
+    ref = 0.5 * xd * (1 + torch.erf(xd / 2 ** 0.5))
+    err = (out.cpu().double() - ref).abs()
+    assert bool((err <= ref.abs() * 2.0 ** -8 + 3e-4 * xd.abs() + 4e-5).all()), float(err.max())
+    exact_rounded = ref.to(torch.bfloat16).double()
+    extra = (out.cpu().double() - exact_rounded).abs()            # beyond the unavoidable rounding
+    rms_extra = float(extra.pow(2).mean().sqrt())
+    rms_round = float((exact_rounded - ref).pow(2).mean().sqrt())
+    print(f"gelu epilogue: rms beyond rounding {rms_extra:.2e}, rounding itself {rms_round:.2e}")
+    assert rms_extra < 0.6 * rms_round + 1e-5
+
+
 def test_gemm_residual_and_patch_embed():
     from vitparticlefiltertracker_b200 import ops
     dev = cuda()

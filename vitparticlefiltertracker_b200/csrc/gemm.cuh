@@ -143,6 +143,33 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   return ffma2(n, e, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
 }
 
+// The same function in 8 instructions per pair, two of them MUFU (the polynomial above: 14):
+//   gelu(x) = 0.5 x (1 + tanh(x (c0 + c1 x^2 + c2 x^4))),  c fitted (minimax, [-9, 9]) to the EXACT
+//   erf-GELU, not the textbook tanh approximation: formula error <= 2.5e-5 absolute (textbook
+//   coefficients: 4.7e-4).  tanh.approx.f32 adds <= 2^-11 relative on tanh, i.e. <= 2.4e-4 |x| on
+//   the result; against fp64 erf-GELU for x ~ N(0, 1) the rms error is 1.2e-4, six times below
+//   the bf16 rounding of the output (7.4e-4 rms) -- noise power +2.6 %.
+// Why it matters: fc1 is the largest kernel of a frame and the only GEMM whose epilogue does real
+// arithmetic; under the power cap every instruction of it is paid in clock (experiments/README.md).
+__device__ __forceinline__ float2 gelu_tanh2(float2 x) {
+  auto k2 = [](float c) { return make_float2(c, c); };
+  const float2 x2 = ffma2(x, x, k2(0.0f));
+  float2 p = ffma2(k2(-3.51516788e-04f), x2, k2(3.70056460e-02f));
+  p = ffma2(p, x2, k2(7.97507884e-01f));
+  const float2 u = ffma2(x, p, k2(0.0f));
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  const float2 hx = ffma2(x, k2(0.5f), k2(0.0f));
+  return ffma2(hx, t, hx);
+}
+#ifndef VPF_GELU_ERF_POLY
+#define VPF_GELU_ERF_POLY 0      // 1: the degree-7 erfc polynomial (A/B builds)
+#endif
+__device__ __forceinline__ float2 gelu2(float2 x) {
+  return VPF_GELU_ERF_POLY ? gelu_erf2(x) : gelu_tanh2(x);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -208,7 +235,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
       }
       if (mode_gelu(MODE)) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) f[e] = gelu_erf2(f[e]);
+        for (int e = 0; e < 4; ++e) f[e] = gelu2(f[e]);
       }
       uint4 o;
       const bool f16 = g.f16 != 0;
