@@ -128,7 +128,49 @@ def kernels(path, out, note=""):
         print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in d.items()})
 
 
+def block(path, tag, note=""):
+    """`ncu --set full` of tools/prof_kernels.py from the crop kernel of step 1 on (crop, patch embed,
+    rowstats, qkv, attention, proj, fc1, fc2, qkv ...) -> profiles/ncu_block_<tag>.json (every launch)
+    and profiles/ncu_gemm_<tag>.json (the GEMM family's DRAM traffic in bench.py's `roofline.traffic`
+    format, stamped with the hash of the GEMM sources and the commit)."""
+    import hashlib
+    kernels(path, f"ncu_block_{tag}", note)
+    launches_ = json.load(open(f"profiles/ncu_block_{tag}.json"))["launches"]
+    esz = 2                                               # fp16 residual stream
+    alg = {"qkv": M * D * 2 + 3 * D * D * 2 + M * 3 * D * 2, "proj": M * D * 2 + D * D * 2 + 2 * M * D * esz,
+           "fc1": M * D * 2 + 4 * D * D * 2 + M * 4 * D * 2, "fc2": M * 4 * D * 2 + 4 * D * D * 2 + 2 * M * D * esz}
+    mode_of = {"qkv": ("<256, 5, 2>", "<256, 0, 2>"), "proj": ("<256, 4, 2>",), "fc1": ("<256, 6, 2>", "<256, 1, 2>"),
+               "fc2": ("<256, 2, 2>",)}
+    res = []
+    for shape, modes in mode_of.items():
+        x = next(l for l in launches_ if any(m in l["kernel"] for m in modes))
+        res.append({"shape": shape, "kernel": x["kernel"][:64], "duration_ms_under_ncu": x["duration_ms"],
+                    "dram_read_bytes": x["dram_read_bytes"], "dram_write_bytes": x["dram_write_bytes"],
+                    "traffic_bytes": x["dram_read_bytes"] + x["dram_write_bytes"], "algorithmic_bytes": alg[shape],
+                    "flops": ALG[shape][1], "tensor_pipe_active_pct": x["tensor_pipe_active_pct"],
+                    "sm_clock_ghz": x["sm_clock_ghz"], "dram_throughput_pct": x["dram_throughput_pct"],
+                    "l2_hit_pct": x["l2_hit_pct"], "issue_active_pct": x["issue_active_pct"],
+                    "registers": x["registers"]})
+    h = hashlib.sha256()
+    for n in ("gemm.cuh", "sm100.cuh"):
+        h.update(open("vitparticlefiltertracker_b200/csrc/" + n, "rb").read())
+    sha = subprocess.run("git rev-parse --short HEAD", shell=True, capture_output=True, text=True).stdout.strip()
+    json.dump({"source": f"ncu --set full --clock-control none --import-source on, tools/prof_kernels.py (1xB200, "
+                         f"ViT-B/16, N=4096, fp16 residual stream, LayerNorm folded into qkv / fc1); {path}",
+               "residual": "fp16", "launches": res,
+               "gemm_family_traffic_bytes_per_block": sum(r["traffic_bytes"] for r in res),
+               "gemm_family_algorithmic_bytes_per_block": sum(alg.values()),
+               "source_sha16": h.hexdigest()[:16], "git_sha": sha},
+              open(f"profiles/ncu_gemm_{tag}.json", "w"), indent=1)
+    for r in res:
+        print(r["shape"], round(r["traffic_bytes"] / 1e9, 2), "GB vs", round(r["algorithmic_bytes"] / 1e9, 2),
+              "tensor %", round(r["tensor_pipe_active_pct"], 1), "GHz", round(r["sm_clock_ghz"], 3))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 3 and sys.argv[1] == "--block":    # --block report.ncu-rep tag [note]
+        block(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
+        sys.exit(0)
     if len(sys.argv) > 3 and sys.argv[1] == "--kernels":  # --kernels report.ncu-rep out_name [note]
         kernels(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
         sys.exit(0)
