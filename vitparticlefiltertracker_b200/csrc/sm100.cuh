@@ -186,9 +186,15 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster (the epilogue warps of a CTA pair hand the
+// drained accumulator back to the leader's MMA thread).  Default semantics (.release at .cta
+// scope), as a single SYNCS.ARRIVE: what is handed over is tensor memory, already ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync.  Spelling it `.release.cluster` makes ptxas
+// emit MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the arrive, which wait for
+// the warp's outstanding GLOBAL stores -- the epilogue's own output -- once per tile: 37 % of the
+// qkv GEMM's stall samples sat on those four instructions (profiles/ncu_block_r02c.json build).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // 2-D TMA load issued by either CTA of a pair: data lands in the issuing CTA's shared memory,
 // completion bytes are counted on the barrier at `bar_cluster_addr` (the pair leader's).
