@@ -459,14 +459,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint64_t* xbar = epi_bar + (warp - 2) * 2;
       uint32_t j = 0;
       const bool x16 = g.x16 != 0;           // fp16 residual: 32 x 32 tile = 2 KB, 64-byte swizzle
-      auto issue_load = [&](int tile_, int c_, uint32_t jj) {
-        const int mb = tile_ / n_blocks, nb = tile_ - mb * n_blocks;
+      auto issue_load = [&](int mb, int nb, int c_, uint32_t jj) {   // (row block, column block)
         mbar_arrive_expect_tx(&xbar[jj & 1], x16 ? 2048u : 4096u);
         tma_load_2d(xbuf + (jj & 1) * 4096, &tmC, &xbar[jj & 1],
                     nb * BLOCK_N + half * kHalfCols + c_ * 32,
                     (mb * CTAS + (int)cta_rank) * kBlockM + quarter * 32);
       };
-      if (lane == 0 && group < n_tiles) issue_load(group, 0, 0);
+      if (lane == 0 && group < n_tiles) issue_load(group / n_blocks, group % n_blocks, 0, 0);
       for (int tile = group; tile < n_tiles; tile += n_groups, ++it) {
         const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
         const int as = it & 1;
@@ -480,11 +479,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
         for (int c = 0; c < kChunks; ++c, ++j) {
           if (lane == 0) {                       // prefetch the next chunk's residual tile
-            int nt = tile, nc = c + 1;
-            if (nc == kChunks) { nt = tile + n_groups; nc = 0; }
-            if (nt < n_tiles) {
+            // next chunk of this tile, or the first chunk of the next tile (one integer division
+            // per tile, not per chunk)
+            int nm = m_blk, nn = n_blk, nc = c + 1;
+            bool more = true;
+            if (nc == kChunks) {
+              const int nt = tile + n_groups;
+              more = nt < n_tiles;
+              nm = nt / n_blocks; nn = nt - nm * n_blocks; nc = 0;
+            }
+            if (more) {
               tma_store_wait_read<0>();          // the other buffer's last store has left smem
-              issue_load(nt, nc, j + 1);
+              issue_load(nm, nn, nc, j + 1);
             }
           }
           __syncwarp();
