@@ -44,6 +44,9 @@ static constexpr int kKVStages = 2;
 static constexpr int kQBytes = 128 * kD * 2;        // 16 KB
 static constexpr int kKVBytes = kKeys * kD * 2;     // 26 KB (1024-byte multiple)
 static constexpr int kThreads = 320;
+// the run-time-token kernel has a second MMA-issuing warp (one per TMEM buffer)
+static constexpr int kThreadsVar = 352;
+static constexpr int kMmaWarp1 = 10;
 static constexpr int kSmemBytes = kQStages * kQBytes + kKVStages * 2 * kKVBytes + 1024 + 256;
 static constexpr int kTmemCols = 512;
 static constexpr int kBufCols = 256;
@@ -415,8 +418,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // alternate between the two TMEM buffers / softmax warpgroups whatever the tile count, so with one
 // tile per pair the two warpgroups work on consecutive pairs.  The T = 197 kernel above stays the
 // specialised (fully unrolled) version of this one.
+// With ONE query tile per pair (T <= 128) there are two MMA-issuing threads, one per TMEM buffer
+// (warps 1 and 10), each walking its own chain S -> PV -> S ... with blocking waits: a single issuer
+// that walks both chains in a fixed order waits for buffer 0's O to be read out while buffer 1's PV
+// is ready.  Measured (N = 4096, 12 heads): T = 101 0.762 -> 0.625 ms, T = 65 0.665 -> 0.531 ms.
+// With TWO tiles per pair the same split is SLOWER (T = 145 1.10 -> 1.28 ms, T = 170 1.31 -> 1.47 ms,
+// the T = 197 kernel 1.087 -> 1.32 ms, with or without an anti-phase start), so those keep the single
+// issuer (experiments/README.md).
 //   TMEM buffer b at column 256 b:  S [0,keys)  P aliases [0,keys/2)  O [128,192)
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsVar, 1)
 attention_tc_var_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         __nv_bfloat16* __restrict__ out, int n_pairs, int heads, int D, int f16_,
                         int T, int keys) {
@@ -483,8 +493,11 @@ attention_tc_var_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tma_load_3d(sQ + qs * kQBytes, &tmQ, &q_full[qs], head * kD, t * 128, crop);
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == kMmaWarp1) {
+    // ===================== MMA issuers =====================
+    // One query tile per pair (T <= 128): warp 1 walks TMEM buffer 0's chain (even units), warp 10
+    // buffer 1's, each S -> PV -> S ... with blocking waits.  Two tiles per pair: warp 1 alone in
+    // the fixed order PV(u), S(u+2), PV(u+1), ... (two issuers are slower there, see above).
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_16(128, keys, f16);
       const uint32_t idesc_o = make_idesc_bmn(128, kD, f16);
@@ -517,11 +530,18 @@ attention_tc_var_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         umma_commit(&o_full[b]);
         if (t == tpp - 1) umma_commit(&kv_empty[ks]);    // every MMA of this pair has retired
       };
-      if (units > 0) issue_s(0);
-      if (units > 1) issue_s(1);
-      for (int u = 0; u < units; ++u) {
-        issue_pv(u);
-        if (u + 2 < units) issue_s(u + 2);
+      if (tpp == 1) {
+        for (int u = (warp == 1 ? 0 : 1); u < units; u += 2) {
+          issue_s(u);
+          issue_pv(u);
+        }
+      } else if (warp == 1) {
+        if (units > 0) issue_s(0);
+        if (units > 1) issue_s(1);
+        for (int u = 0; u < units; ++u) {
+          issue_pv(u);
+          if (u + 2 < units) issue_s(u + 2);
+        }
       }
     }
   } else {

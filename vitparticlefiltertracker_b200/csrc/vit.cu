@@ -597,7 +597,7 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_
       if (first_time_on_device(attr))
         VPF_CUDA(cudaFuncSetAttribute(attn::attention_tc_var_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, attn::kSmemBytes));
-      VPF_CUDA(launch_pdl(pdl, attn::attention_tc_var_kernel, dim3(grid), dim3(attn::kThreads),
+      VPF_CUDA(launch_pdl(pdl, attn::attention_tc_var_kernel, dim3(grid), dim3(attn::kThreadsVar),
                           (size_t)attn::kSmemBytes, s, *mq, *mkv, out, n_pairs, heads, D, f16, tokens,
                           keys_padded(tokens)));
     }
