@@ -201,17 +201,19 @@ def ncu_traffic(residual):
     source stamp matches the GEMM sources of this build and whose residual-stream type is the
     one being run; (None, why) otherwise."""
     cur = source_hash("gemm.cuh", "sm100.cuh")
-    for name in ("ncu_gemm_r02c.json", "ncu_gemm_r02b.json", "ncu_gemm_r02.json", "ncu_gemm_r01.json"):
+    for name in ("ncu_gemm_r02e.json", "ncu_gemm_r02c.json", "ncu_gemm_r02b.json", "ncu_gemm_r02.json",
+                 "ncu_gemm_r01.json"):
         prof = os.path.join(ROOT, "profiles", name)
         if not os.path.exists(prof):
             continue
         pj = json.load(open(prof))
         if pj.get("source_sha16") != cur or pj.get("residual", "fp32") != residual:
             continue
+        how = pj.get("traffic_note") or ("dram__bytes_read+write summed over the four launches of one "
+                                         "block (ncu --set full)")
         return (pj["gemm_family_traffic_bytes_per_block"],
-                f"profiles/{name} (capture of git {pj.get('git_sha', '?')}, source stamp {cur}): "
-                "dram__bytes_read+write summed over the four launches of one block (ncu --set "
-                f"full); algorithmic bytes {pj['gemm_family_algorithmic_bytes_per_block']:.4g}")
+                f"profiles/{name} (capture of git {pj.get('git_sha', '?')}, source stamp {cur}): {how}; "
+                f"algorithmic bytes {pj['gemm_family_algorithmic_bytes_per_block']:.4g}")
     return None, f"no committed ncu capture matches this build's GEMM sources (stamp {cur})"
 
 
