@@ -42,7 +42,8 @@ def main(path="config.yaml"):
                   cuda_graph=bool(cfg.get("cuda_graph", False)),
                   crop_size=int(cfg.get("crop_size", 224)),
                   residual_dtype=torch.float32 if cfg.get("residual_dtype", "fp16") == "fp32"
-                  else torch.float16)
+                  else torch.float16,
+                  ln_fold=cfg.get("ln_fold"))      # None: folded whenever the stream is fp16
     frames = iter(frames)
     trk.init(next(frames), bbox)
     t0 = time.perf_counter()
