@@ -201,7 +201,7 @@ def ncu_traffic(residual):
     source stamp matches the GEMM sources of this build and whose residual-stream type is the
     one being run; (None, why) otherwise."""
     cur = source_hash("gemm.cuh", "sm100.cuh")
-    for name in ("ncu_gemm_r02e.json", "ncu_gemm_r02c.json", "ncu_gemm_r02b.json", "ncu_gemm_r02.json",
+    for name in ("ncu_gemm_r02f.json", "ncu_gemm_r02e.json", "ncu_gemm_r02c.json", "ncu_gemm_r02b.json", "ncu_gemm_r02.json",
                  "ncu_gemm_r01.json"):
         prof = os.path.join(ROOT, "profiles", name)
         if not os.path.exists(prof):

@@ -51,6 +51,18 @@ struct GemmArgs {
   const float* pos;
   int f16 = 0;   // 16-bit operand / output type: 0 = bf16, 1 = fp16
   int ppc = 196; // patch-embed mode: patches per crop (196 at crop size 224); tokens = ppc + 1
+  // row / ppc without a division (the epilogue needs it 32 times per thread and tile):
+  // floor(n / ppc) = umulhi(n, ppc_mul) >> ppc_shift for every n < 2^31 (set_ppc); ppc == 1: n
+  unsigned ppc_mul = 0, ppc_shift = 0;
+  void set_ppc(int p) {
+    ppc = p;
+    if (p <= 1) { ppc_mul = 0; ppc_shift = 0; return; }
+    int k = 0;
+    while ((1 << k) < p) ++k;                              // ceil(log2 p) >= 1
+    const unsigned long long two_s = 1ull << (31 + k);
+    ppc_mul = (unsigned)((two_s + (unsigned long long)p - 1) / (unsigned long long)p);   // < 2^32
+    ppc_shift = (unsigned)(k - 1);                         // (31 + k) - 32
+  }
   int x16 = 0;   // residual modes: the residual stream X is fp16 (saturating) instead of fp32
   // LayerNorm-folded modes (5, 6): the row statistics of A.
   //   stats_parts == 0: stats[r * stats_stride] = (mu, r) final;
@@ -285,7 +297,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
       dst[i] = nullptr;
       if (grow < g.M) {
         if (MODE == kPatchEmbedF32) {
-          const int crop = grow / g.ppc, pp = grow - crop * g.ppc;
+          const int crop = g.ppc_mul ? (int)(__umulhi((unsigned)grow, g.ppc_mul) >> g.ppc_shift) : grow;
+          const int pp = grow - crop * g.ppc;
           dst[i] = X + ((((size_t)crop * (g.ppc + 1) + 1 + pp) * g.N + col) + 4 * p) * esz;
           res[i] = __ldg(reinterpret_cast<const float4*>(g.pos + (size_t)(1 + pp) * g.N + col) + p);
         } else {

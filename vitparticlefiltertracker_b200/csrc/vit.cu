@@ -1173,7 +1173,7 @@ int vpf_vit_forward(vpf_vit* h, const void* patches, int n, float* emb, void* st
                         h->pos, n, D, T, h->x16));
     GemmArgs g{M0, D, 768, h->patch_b, h->X, h->pos};
     g.f16 = h->cfg.dtype == VPF_DTYPE_F16;
-    g.ppc = h->ppc;
+    g.set_ppc(h->ppc);
     g.x16 = h->x16;
     if ((rc = launch_gemm(h->a_patches, h->m_patch, g, kPatchEmbedF32, s))) return rc;
   }
@@ -1222,7 +1222,7 @@ int vpf_gemm_bf16(const void* A, const void* W, const float* bias, void* out, co
   if ((rc = make_map(&ma, A, M, K, kBlockM))) return rc;
   if ((rc = make_map(&mb, W, N, K, bn / gemm_ctas()))) return rc;
   GemmArgs g{M, N, K, bias, out, pos};
-  if (mode == kPatchEmbedF32) g.ppc = patches_per_crop;
+  if (mode == kPatchEmbedF32) g.set_ppc(patches_per_crop);
   g.x16 = (mode >= kBiasResidualF32 && residual_dtype == VPF_RESIDUAL_F16) ? 1 : 0;
   return launch_gemm(ma, mb, g, mode, (cudaStream_t)stream);
 }
